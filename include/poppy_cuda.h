@@ -1,0 +1,129 @@
+/* poppy_cuda.h — C ABI of the B200 (sm_100a) morph renderer.
+ *
+ * This is the device boundary of the drop-in for the reference's per-frame morph path. The reference has no
+ * FFI for this path: the boundary there is the in-process C++ call
+ *     double poppy::morph_images(...)                       (reference src/algo.hpp:26, src/algo.cpp:178-273)
+ * configured by poppy::Settings::pyramid_levels             (reference src/settings.hpp:20, read at algo.cpp:261)
+ * and driven by the frame loop of poppy::morph<Twriter>()   (reference src/poppy.hpp:177-243).
+ * The retained C++ host shim (poppy_b200/csrc/host/morph_images.hpp, same signature semantics) performs the host
+ * stages (clip_points / make_uniq / Delaunay topology / vertex index lookup, reference src/algo.cpp:184-213)
+ * and calls the functions below for everything from morph_points() to the final 8-bit frame
+ * (reference src/algo.cpp:202, 216-265; src/blend.hpp:11-91; src/util.cpp:113-148).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * poppy_cuda_status; no C++ exception crosses this line; there is NO CPU fallback — without a CUDA device
+ * poppy_cuda_create fails with POPPY_CUDA_ERR_NO_DEVICE. One context per GPU, driven by one host thread;
+ * calls on distinct contexts are thread-safe. Host buffers are caller-owned (pinned memory makes the copies
+ * asynchronous); all device memory is owned by the context.
+ */
+#ifndef POPPY_CUDA_H_
+#define POPPY_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct poppy_cuda_ctx poppy_cuda_ctx;
+
+typedef enum poppy_cuda_status {
+    POPPY_CUDA_OK = 0,
+    POPPY_CUDA_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the path does not run */
+    POPPY_CUDA_ERR_INVALID = -2,     /* bad argument (null pointer, size out of range, index out of range) */
+    POPPY_CUDA_ERR_CAPACITY = -3,    /* more points / triangles / frames than the context was created for */
+    POPPY_CUDA_ERR_STATE = -4,       /* call sequence error (render before set_pair / set_points, ...) */
+    POPPY_CUDA_ERR_CUDA = -5         /* a CUDA runtime call failed; see poppy_cuda_last_error */
+} poppy_cuda_status;
+
+/* Stage buffers that poppy_cuda_debug_read can fetch (context created with keep_stages != 0).
+ * They are the stage boundaries of reference src/algo.cpp:202-265. */
+typedef enum poppy_cuda_stage {
+    POPPY_STAGE_MORPHED_POINTS = 0,  /* n x 2 float            morph_points + clip_points, algo.cpp:202-205      */
+    POPPY_STAGE_TRI_MAP = 1,         /* h x w int32            paint_triangles, algo.cpp:222-223                 */
+    POPPY_STAGE_INV_M1 = 2,          /* T x 9 float            inv(morphHom1[k]) as create_map applies it, :154-157 */
+    POPPY_STAGE_INV_M2 = 3,          /* T x 9 float            inv(morphHom2[k])                                  */
+    POPPY_STAGE_WARPED1 = 4,         /* h x w x 3 uint8        remap(corrected1), algo.cpp:233                    */
+    POPPY_STAGE_WARPED2 = 5,         /* h x w x 3 uint8        remap(corrected2), algo.cpp:238                    */
+    POPPY_STAGE_MASK = 6,            /* h x w float            lbmask, algo.cpp:250-258                           */
+    POPPY_STAGE_LAP_BLEND = 7        /* h x w x 3 float (BGR interleaved)  LaplacianBlending::blend(), :261-262   */
+} poppy_cuda_stage;
+
+int poppy_cuda_device_count(void);
+
+/* width/height: frame size (both < 32767, as cv::remap requires). pyramid_levels: Settings::pyramid_levels
+ * (any value >= 1; levels past 1x1 stay 1x1 exactly as cv::pyrDown/pyrUp do). max_points / max_triangles /
+ * max_batch_frames bound set_points, render and the HBM frame ring. */
+int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, int pyramid_levels, int max_points,
+                      int max_triangles, int max_batch_frames);
+void poppy_cuda_destroy(poppy_cuda_ctx* ctx);
+
+/* Options; call before the first render. */
+int poppy_cuda_set_keep_stages(poppy_cuda_ctx* ctx, int keep);       /* 1: chunk size 1, stage buffers readable */
+int poppy_cuda_set_chunk_frames(poppy_cuda_ctx* ctx, int frames);    /* frames rendered per kernel batch (>=1) */
+int poppy_cuda_set_stage_timing(poppy_cuda_ctx* ctx, int enable);    /* CUDA-event timing per kernel class */
+
+/* corrected1 / corrected2 (8UC3 BGR, row stride in bytes) and gabor2 (32FC3 BGR in [0,1], row stride in bytes) of
+ * one image pair: the Mat arguments of morph_images (reference src/algo.cpp:178). H2D once per pair. */
+int poppy_cuda_set_pair(poppy_cuda_ctx* ctx, const uint8_t* bgr1, size_t step1, const uint8_t* bgr2, size_t step2,
+                        const float* gabor2_bgr32f, size_t gstep);
+
+/* srcPoints1 / srcPoints2 (n x 2 float, x then y), unclipped as the caller holds them. */
+int poppy_cuda_set_points(poppy_cuda_ctx* ctx, const float* pts1_xy, const float* pts2_xy, int n);
+
+/* Render n_frames frames into the HBM frame ring (slots 0 .. n_frames-1).
+ * shape_ratio[f], mask_ratio[f]: the shapeRatio / maskRatio arguments of morph_images for frame f.
+ * tri_idx: concatenated triangle vertex indices (3 per triangle, indices into the point sets) of every frame's
+ * Delaunay mesh of the *morphed* points, in cv::Subdiv2D::getTriangleList order (this order decides which
+ * triangle wins a shared pixel, reference src/algo.cpp:95-106); tri_offsets[f] .. tri_offsets[f+1] delimit frame f
+ * (in triangles).
+ * chain == 0: every frame is rendered from the pair and point sets as uploaded (direct mode; the reference's
+ *             "-f 1 -p s" frame, src/poppy.hpp:186-200).
+ * chain == 1: frame f>0 takes frame f-1's output as corrected1 and frame f-1's morphed points as srcPoints1
+ *             (the recurrence of the reference frame loop, src/poppy.hpp:178-179,217-218).
+ * Asynchronous with respect to the device; host arrays are consumed before the call returns. */
+int poppy_cuda_render(poppy_cuda_ctx* ctx, int n_frames, const float* shape_ratio, const double* mask_ratio,
+                      const int32_t* tri_idx, const int32_t* tri_offsets, int chain);
+
+/* Copy frames [first, first+count) (8UC3 BGR) to host memory: row stride `step` bytes, `frame_stride` bytes
+ * between frames. Asynchronous if dst is pinned; poppy_cuda_sync() before reading. */
+int poppy_cuda_download(poppy_cuda_ctx* ctx, int first, int count, uint8_t* dst, size_t step, size_t frame_stride);
+
+/* morphedPoints of frame `frame` of the last render (n x 2 float) — the out-parameter of morph_images. */
+int poppy_cuda_get_morphed_points(poppy_cuda_ctx* ctx, int frame, float* xy);
+
+/* Device address of frame slot `frame` (8UC3, tightly packed rows) for zero-copy consumers; *bytes = frame size. */
+int poppy_cuda_frame_device_ptr(poppy_cuda_ctx* ctx, int frame, void** dptr, size_t* bytes);
+
+/* 64-bit FNV-1a style checksum of frames [first, first+count) computed on the device (order dependent). */
+int poppy_cuda_checksum(poppy_cuda_ctx* ctx, int first, int count, uint64_t* out);
+
+int poppy_cuda_sync(poppy_cuda_ctx* ctx);
+
+/* The CUDA stream every launch of this context goes to (cudaStream_t), for event timing by the caller. */
+int poppy_cuda_get_stream(poppy_cuda_ctx* ctx, void** stream);
+
+/* Device time (ms, CUDA events on the context's stream) of the last poppy_cuda_render call; syncs. */
+int poppy_cuda_last_render_ms(poppy_cuda_ctx* ctx, float* ms);
+
+/* Kernel launches issued by this context since creation (its own kernels only, memsets/copies not counted). */
+int poppy_cuda_launch_count(poppy_cuda_ctx* ctx, uint64_t* launches);
+
+/* Per-kernel-class device time of the last render (stage timing enabled). Fills up to `cap` entries; returns the
+ * number of classes. names[i] points to a static string. */
+int poppy_cuda_stage_times(poppy_cuda_ctx* ctx, const char** names, float* ms, uint64_t* launches, int cap);
+
+/* Fetch a stage buffer of frame `frame` of the last render (keep_stages contexts only). `bytes` must match. */
+int poppy_cuda_debug_read(poppy_cuda_ctx* ctx, int stage, int frame, void* dst, size_t bytes);
+
+/* Last error text of this context (or of the failed create when ctx == NULL). */
+const char* poppy_cuda_last_error(const poppy_cuda_ctx* ctx);
+
+/* Build identification: "poppy_cuda <version> sm_100a". */
+const char* poppy_cuda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POPPY_CUDA_H_ */

@@ -1,0 +1,52 @@
+// Host-callable launchers of the device kernels (one per kernel class). All launches go to the given stream.
+#pragma once
+
+#include "common.cuh"
+
+namespace poppy {
+
+// ---- kernels_geometry.cu -----------------------------------------------------------------------------------------
+void launch_clip_points(cudaStream_t st, const float2* in, float2* out, int n, int cols, int rows);
+void launch_lerp_points(cudaStream_t st, const float2* p1, size_t p1_frame_stride, const float2* p2,
+                        const FrameParams* fp, float2* out, size_t out_frame_stride, int n, int frames, int cols,
+                        int rows);
+void launch_tri_geometry(cudaStream_t st, const int3* tri_idx, const FrameParams* fp, const float2* p1,
+                         size_t p1_frame_stride, const float2* p2, const float2* morphed, size_t morphed_frame_stride,
+                         int max_tri, int tri_in_chunk_max, int frames, int img_h, TriInverse* inv_out,
+                         TriRaster* rast_out);
+void launch_raster_triangles(cudaStream_t st, const TriRaster* rast, const FrameParams* fp, int max_tri,
+                             int tri_in_chunk_max, int frames, int* tri_map, int w, int h);
+
+// ---- kernels_warp.cu ---------------------------------------------------------------------------------------------
+// BGR (3 bytes/px, tight rows) -> BGRX uchar4
+void launch_bgr_to_bgrx(cudaStream_t st, const uint8_t* bgr, uchar4* out, int w, int h);
+// mask basis m2 = 1 - gray(gabor2)  (reference src/algo.cpp:250-252)
+void launch_mask_basis(cudaStream_t st, const float* gabor_bgr, float* m2, int w, int h);
+// create_map + remap for both images + lbmask of the frame (reference src/algo.cpp:232-238, 255-258).
+void launch_warp(cudaStream_t st, const int* tri_map, const TriInverse* inv, int max_tri, const uchar4* src1,
+                 const uchar4* src2, const float* mask_basis, const FrameParams* fp, uint2* warped, float* mask0,
+                 int w, int h, int frames);
+
+// ---- kernels_pyramid.cu ------------------------------------------------------------------------------------------
+// level 0 -> 1: sources are the warped 8-bit pair (converted on the fly, algo.cpp:247-248) and mask0
+void launch_pyr_down0(cudaStream_t st, const uint2* warped, const float* mask0, int w, int h, float* dst,
+                      LevelDesc dl, int frames);
+// level k -> k+1 for the 7 planes (left BGR, right BGR, mask)
+void launch_pyr_down(cudaStream_t st, const float* src, LevelDesc sl, float* dst, LevelDesc dl, int frames);
+// resultSmallest = left*mask + right*(1-mask) at the coarsest level (blend.hpp:68-69)
+void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* out, int frames);
+// out[k] = pyrUp(out[k+1]) + (G_l[k]-pyrUp(G_l[k+1]))*m[k] + (G_r[k]-pyrUp(G_r[k+1]))*(1-m[k])   (blend.hpp:45-77)
+void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
+                     LevelDesc cl, float* out_fine, int frames);
+// same for level 0, whose Gaussian level is the warped 8-bit pair + mask0
+void launch_collapse0(cudaStream_t st, const uint2* warped, const float* mask0, int w, int h, const float* g_coarse,
+                      const float* out_coarse, LevelDesc cl, float* out_fine, LevelDesc ol, int frames);
+
+// ---- kernels_unsharp.cu ------------------------------------------------------------------------------------------
+// unsharp_mask(lapBlend, 1, amount, 0.3) + convertTo(CV_8U, 255)   (reference src/algo.cpp:263-265, util.cpp:113-148)
+void launch_unsharp_store(cudaStream_t st, const float* lap_blend, LevelDesc l, const FrameParams* fp,
+                          uint8_t* frames_base, size_t frame_bytes, int frames);
+// order-dependent checksum of a byte range
+void launch_checksum(cudaStream_t st, const uint8_t* data, size_t bytes, unsigned long long* out);
+
+}  // namespace poppy

@@ -1,0 +1,590 @@
+// poppy_cuda.cu — context, HBM layout and the extern "C" layer declared in include/poppy_cuda.h.
+//
+// HBM layout per context (W x H frame, L pyramid levels, chunk of B frames in flight):
+//   pair (resident)   : src1, src2 as BGRX uchar4 [H][W]; mask basis m2 float [H][W]; clipped point sets
+//   frame ring        : max_batch_frames x [H][W*3] 8-bit BGR — the rendered frames stay in HBM until downloaded
+//   morphed points    : max_batch_frames x max_points float2
+//   chunk scratch (xB): FrameParams; triangle indices; TriInverse / TriRaster records; triangle-ID map int32 [H][W];
+//                       warped pair uint2 [H][W]; mask plane float [H][W]; Gaussian levels 1..L (7 planes);
+//                       collapsed levels 0..L (3 planes)
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/poppy_cuda.h"
+#include "device/kernels.cuh"
+
+using namespace poppy;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum KernelClass { KC_POINTS = 0, KC_GEOMETRY, KC_RASTER, KC_WARP, KC_PYR_DOWN, KC_COLLAPSE, KC_UNSHARP, KC_MISC, KC_COUNT };
+const char* const kClassNames[KC_COUNT] = {"lerp_points", "tri_geometry", "raster_triangles", "warp_sample",
+                                           "pyr_down", "blend_collapse", "unsharp_store", "misc"};
+
+struct TimedLaunch { int cls; cudaEvent_t a, b; };
+
+}  // namespace
+
+struct poppy_cuda_ctx {
+    int device = 0, w = 0, h = 0, levels = 0, max_points = 0, max_tri = 0, max_frames = 0;
+    int chunk = 0;            // frames per kernel batch (0 = not yet allocated)
+    int want_chunk = 0;
+    bool keep_stages = false, stage_timing = false;
+    bool have_pair = false, have_points = false;
+    int n_points = 0, last_frames = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_stage[2] = {nullptr, nullptr};
+    std::string err;
+    uint64_t launches = 0;
+
+    std::vector<LevelDesc> lv;           // level 0 .. L
+    std::vector<size_t> g_off, o_off;    // float offsets of level k inside d_g / d_o for ONE frame-chunk block
+    size_t g_floats = 0, o_floats = 0;   // per chunk
+
+    // resident
+    uchar4 *d_src1 = nullptr, *d_src2 = nullptr, *d_src_chain = nullptr;
+    float* d_mbasis = nullptr;
+    float2 *d_pts1_raw = nullptr, *d_pts2_raw = nullptr, *d_pts1 = nullptr, *d_pts2 = nullptr, *d_morphed = nullptr;
+    uint8_t* d_frames = nullptr;
+    unsigned long long* d_sum = nullptr;
+    // chunk scratch
+    FrameParams* d_fp = nullptr;
+    int3* d_tri = nullptr;
+    TriInverse* d_inv = nullptr;
+    TriRaster* d_rast = nullptr;
+    int* d_trimap = nullptr;
+    uint2* d_warped = nullptr;
+    float *d_mask0 = nullptr, *d_g = nullptr, *d_o = nullptr;
+    // pinned staging, double buffered
+    FrameParams* h_fp[2] = {nullptr, nullptr};
+    int32_t* h_tri[2] = {nullptr, nullptr};
+
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    float class_ms[KC_COUNT] = {0};
+    uint64_t class_launches[KC_COUNT] = {0};
+
+    size_t frame_bytes() const { return (size_t)w * h * 3; }
+    size_t pixels() const { return (size_t)w * h; }
+};
+
+namespace {
+
+int fail(poppy_cuda_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU_TRY(c, expr)                                                                                     \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail((c), POPPY_CUDA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T> cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
+
+void free_chunk(poppy_cuda_ctx* c) {
+    cudaFree(c->d_fp); cudaFree(c->d_tri); cudaFree(c->d_inv); cudaFree(c->d_rast); cudaFree(c->d_trimap);
+    cudaFree(c->d_warped); cudaFree(c->d_mask0); cudaFree(c->d_g); cudaFree(c->d_o);
+    for (int i = 0; i < 2; ++i) { cudaFreeHost(c->h_fp[i]); cudaFreeHost(c->h_tri[i]); c->h_fp[i] = nullptr; c->h_tri[i] = nullptr; }
+    c->d_fp = nullptr; c->d_tri = nullptr; c->d_inv = nullptr; c->d_rast = nullptr; c->d_trimap = nullptr;
+    c->d_warped = nullptr; c->d_mask0 = nullptr; c->d_g = nullptr; c->d_o = nullptr;
+    c->chunk = 0;
+}
+
+size_t per_frame_scratch_bytes(const poppy_cuda_ctx* c) {
+    return c->pixels() * (4 + 8 + 4) + (c->g_floats + c->o_floats) * 4 +
+           (size_t)c->max_tri * (sizeof(int3) + sizeof(TriInverse) + sizeof(TriRaster));
+}
+
+int ensure_chunk(poppy_cuda_ctx* c) {
+    int want = c->keep_stages ? 1 : c->want_chunk;
+    if (want <= 0) {
+        // default: keep the chunk scratch under ~6 GiB and give the small pyramid levels enough CTAs
+        size_t per = per_frame_scratch_bytes(c);
+        want = (int)std::min<size_t>(16, std::max<size_t>(1, (6ull << 30) / std::max<size_t>(per, 1)));
+    }
+    want = std::max(1, std::min(want, c->max_frames));
+    if (c->chunk == want) return 0;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    free_chunk(c);
+    const size_t B = want;
+    CU_TRY(c, dmalloc(&c->d_fp, B));
+    CU_TRY(c, dmalloc(&c->d_tri, B * c->max_tri));
+    CU_TRY(c, dmalloc(&c->d_inv, B * c->max_tri));
+    CU_TRY(c, dmalloc(&c->d_rast, B * c->max_tri));
+    CU_TRY(c, dmalloc(&c->d_trimap, B * c->pixels()));
+    CU_TRY(c, dmalloc(&c->d_warped, B * c->pixels()));
+    CU_TRY(c, dmalloc(&c->d_mask0, B * c->pixels()));
+    CU_TRY(c, dmalloc(&c->d_g, B * c->g_floats));
+    CU_TRY(c, dmalloc(&c->d_o, B * c->o_floats));
+    for (int i = 0; i < 2; ++i) {
+        CU_TRY(c, cudaMallocHost((void**)&c->h_fp[i], B * sizeof(FrameParams)));
+        CU_TRY(c, cudaMallocHost((void**)&c->h_tri[i], std::max<size_t>(B * c->max_tri, 1) * 3 * sizeof(int32_t)));
+    }
+    c->chunk = want;
+    return 0;
+}
+
+// level k block of a chunk: all frames' planes of that level are contiguous
+float* g_level(poppy_cuda_ctx* c, int k) { return c->d_g + c->g_off[k] * c->chunk; }
+float* o_level(poppy_cuda_ctx* c, int k) { return c->d_o + c->o_off[k] * c->chunk; }
+
+cudaEvent_t get_event(poppy_cuda_ctx* c) {
+    if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct Scope {   // counts a launch and, when stage timing is on, brackets it with events
+    poppy_cuda_ctx* c; int cls; TimedLaunch t{};
+    Scope(poppy_cuda_ctx* c_, int cls_) : c(c_), cls(cls_) {
+        c->launches++;
+        c->class_launches[cls]++;
+        if (c->stage_timing) { t.cls = cls; t.a = get_event(c); t.b = get_event(c); cudaEventRecord(t.a, c->stream); }
+    }
+    ~Scope() {
+        if (c->stage_timing) { cudaEventRecord(t.b, c->stream); c->timed.push_back(t); }
+    }
+};
+
+void collect_timing(poppy_cuda_ctx* c) {
+    for (auto& t : c->timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) c->class_ms[t.cls] += ms;
+        c->event_pool.push_back(t.a);
+        c->event_pool.push_back(t.b);
+    }
+    c->timed.clear();
+}
+
+int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const double* mask, const int32_t* tri_idx,
+                 const int32_t* tri_off, bool chain, int slot) {
+    cudaStream_t st = c->stream;
+    CU_TRY(c, cudaEventSynchronize(c->ev_stage[slot]));       // staging buffers of this slot are free again
+    FrameParams* hp = c->h_fp[slot];
+    int32_t* ht = c->h_tri[slot];
+    int tri_total = 0, tri_max = 0;
+    for (int i = 0; i < nb; ++i) {
+        const int f = first + i;
+        const int nt = tri_off[f + 1] - tri_off[f];
+        if (nt < 0 || nt > c->max_tri) return fail(c, POPPY_CUDA_ERR_CAPACITY, "frame %d has %d triangles (max %d)", f, nt, c->max_tri);
+        const int32_t* src = tri_idx + (size_t)tri_off[f] * 3;
+        for (int j = 0; j < nt * 3; ++j)
+            if ((unsigned)src[j] >= (unsigned)c->n_points)
+                return fail(c, POPPY_CUDA_ERR_INVALID, "frame %d: vertex index %d out of range [0,%d)", f, src[j], c->n_points);
+        std::memcpy(ht + (size_t)tri_total * 3, src, (size_t)nt * 3 * sizeof(int32_t));
+        FrameParams& p = hp[i];
+        p.shape = shape[f];
+        p.one_minus_r = (float)(1.0 - (double)p.shape);
+        p.mask_alpha = 1.0 - mask[f];
+        p.mask_beta = -mask[f];
+        p.amount = (float)(1.0 - std::sin(mask[f] * M_PI));
+        p.n_tri = nt;
+        p.tri_base = tri_total;
+        p.dst_slot = f;
+        tri_total += nt;
+        tri_max = std::max(tri_max, nt);
+    }
+    CU_TRY(c, cudaMemcpyAsync(c->d_fp, hp, nb * sizeof(FrameParams), cudaMemcpyHostToDevice, st));
+    if (tri_total) CU_TRY(c, cudaMemcpyAsync(c->d_tri, ht, (size_t)tri_total * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU_TRY(c, cudaEventRecord(c->ev_stage[slot], st));
+
+    const bool chained = chain && first > 0;
+    const float2* p1 = chained ? c->d_morphed + (size_t)(first - 1) * c->max_points : c->d_pts1;
+    const uchar4* src1 = chained ? c->d_src_chain : c->d_src1;
+    float2* morphed = c->d_morphed + (size_t)first * c->max_points;
+    const int n = c->n_points, w = c->w, h = c->h, L = c->levels;
+
+    {   Scope s(c, KC_POINTS);
+        launch_lerp_points(st, p1, 0, c->d_pts2, c->d_fp, morphed, c->max_points, n, nb, w, h);
+    }
+    {   Scope s(c, KC_GEOMETRY);
+        launch_tri_geometry(st, c->d_tri, c->d_fp, p1, 0, c->d_pts2, morphed, c->max_points, c->max_tri, tri_max, nb, h,
+                            c->d_inv, c->d_rast);
+    }
+    CU_TRY(c, cudaMemsetAsync(c->d_trimap, 0, (size_t)nb * c->pixels() * sizeof(int), st));
+    {   Scope s(c, KC_RASTER);
+        launch_raster_triangles(st, c->d_rast, c->d_fp, c->max_tri, tri_max, nb, c->d_trimap, w, h);
+    }
+    {   Scope s(c, KC_WARP);
+        launch_warp(st, c->d_trimap, c->d_inv, c->max_tri, src1, c->d_src2, c->d_mbasis, c->d_fp, c->d_warped,
+                    c->d_mask0, w, h, nb);
+    }
+    {   Scope s(c, KC_PYR_DOWN);
+        launch_pyr_down0(st, c->d_warped, c->d_mask0, w, h, g_level(c, 1), c->lv[1], nb);
+    }
+    for (int k = 1; k < L; ++k) {
+        Scope s(c, KC_PYR_DOWN);
+        launch_pyr_down(st, g_level(c, k), c->lv[k], g_level(c, k + 1), c->lv[k + 1], nb);
+    }
+    {   Scope s(c, KC_COLLAPSE);
+        launch_blend_coarsest(st, g_level(c, L), c->lv[L], o_level(c, L), nb);
+    }
+    for (int k = L - 1; k >= 1; --k) {
+        Scope s(c, KC_COLLAPSE);
+        launch_collapse(st, g_level(c, k), c->lv[k], g_level(c, k + 1), o_level(c, k + 1), c->lv[k + 1], o_level(c, k), nb);
+    }
+    {   Scope s(c, KC_COLLAPSE);
+        launch_collapse0(st, c->d_warped, c->d_mask0, w, h, g_level(c, 1), o_level(c, 1), c->lv[1], o_level(c, 0),
+                         c->lv[0], nb);
+    }
+    {   Scope s(c, KC_UNSHARP);
+        launch_unsharp_store(st, o_level(c, 0), c->lv[0], c->d_fp, c->d_frames, c->frame_bytes(), nb);
+    }
+    if (chain) {
+        Scope s(c, KC_MISC);
+        launch_bgr_to_bgrx(st, c->d_frames + (size_t)(first + nb - 1) * c->frame_bytes(), c->d_src_chain, w, h);
+    }
+    CU_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+const char* poppy_cuda_version(void) { return "poppy_cuda 0.1 sm_100a"; }
+
+int poppy_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* poppy_cuda_last_error(const poppy_cuda_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, int pyramid_levels, int max_points,
+                      int max_triangles, int max_batch_frames) {
+    if (!out) return fail(nullptr, POPPY_CUDA_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || width >= 32767 || height >= 32767)
+        return fail(nullptr, POPPY_CUDA_ERR_INVALID, "frame size %dx%d out of range (cv::remap needs < 32767)", width, height);
+    if (pyramid_levels < 1 || max_points < 3 || max_triangles < 1 || max_batch_frames < 1)
+        return fail(nullptr, POPPY_CUDA_ERR_INVALID, "pyramid_levels/max_points/max_triangles/max_batch_frames out of range");
+    int ndev = poppy_cuda_device_count();
+    if (ndev <= 0) return fail(nullptr, POPPY_CUDA_ERR_NO_DEVICE, "no CUDA device: the morph renderer has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, POPPY_CUDA_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
+    poppy_cuda_ctx* c = new poppy_cuda_ctx();
+    c->device = device; c->w = width; c->h = height; c->levels = pyramid_levels;
+    c->max_points = max_points; c->max_tri = max_triangles; c->max_frames = max_batch_frames;
+    auto bail = [&](int rc) { g_create_error = c->err; poppy_cuda_destroy(c); return rc; };
+#define CR_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+        fail(c, POPPY_CUDA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(POPPY_CUDA_ERR_CUDA); } } while (0)
+    CR_TRY(cudaSetDevice(device));
+    CR_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CR_TRY(cudaEventCreate(&c->ev_begin));
+    CR_TRY(cudaEventCreate(&c->ev_end));
+    for (int i = 0; i < 2; ++i) CR_TRY(cudaEventCreateWithFlags(&c->ev_stage[i], cudaEventDisableTiming));
+    // pyramid geometry: (n+1)/2 per level, 1x1 levels repeat (cv::pyrDown, pyramids.cpp:1260-1303)
+    c->lv.resize(pyramid_levels + 1);
+    c->g_off.assign(pyramid_levels + 2, 0);
+    c->o_off.assign(pyramid_levels + 2, 0);
+    int lw = width, lh = height;
+    for (int k = 0; k <= pyramid_levels; ++k) {
+        LevelDesc& d = c->lv[k];
+        d.w = lw; d.h = lh; d.pitch = (lw + 31) & ~31; d.plane_stride = (size_t)d.pitch * lh;
+        c->g_off[k] = c->g_floats;
+        c->o_off[k] = c->o_floats;
+        if (k >= 1) c->g_floats += 7 * d.plane_stride;
+        c->o_floats += 3 * d.plane_stride;
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+    }
+    const size_t px = c->pixels();
+    CR_TRY(dmalloc(&c->d_src1, px));
+    CR_TRY(dmalloc(&c->d_src2, px));
+    CR_TRY(dmalloc(&c->d_src_chain, px));
+    CR_TRY(dmalloc(&c->d_mbasis, px));
+    CR_TRY(dmalloc(&c->d_pts1_raw, (size_t)max_points));
+    CR_TRY(dmalloc(&c->d_pts2_raw, (size_t)max_points));
+    CR_TRY(dmalloc(&c->d_pts1, (size_t)max_points));
+    CR_TRY(dmalloc(&c->d_pts2, (size_t)max_points));
+    CR_TRY(dmalloc(&c->d_morphed, (size_t)max_points * max_batch_frames));
+    CR_TRY(dmalloc(&c->d_frames, c->frame_bytes() * max_batch_frames));
+    CR_TRY(dmalloc(&c->d_sum, (size_t)1));
+#undef CR_TRY
+    *out = c;
+    return 0;
+}
+
+void poppy_cuda_destroy(poppy_cuda_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    collect_timing(c);
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    free_chunk(c);
+    cudaFree(c->d_src1); cudaFree(c->d_src2); cudaFree(c->d_src_chain); cudaFree(c->d_mbasis);
+    cudaFree(c->d_pts1_raw); cudaFree(c->d_pts2_raw); cudaFree(c->d_pts1); cudaFree(c->d_pts2); cudaFree(c->d_morphed);
+    cudaFree(c->d_frames); cudaFree(c->d_sum);
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    for (int i = 0; i < 2; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int poppy_cuda_set_keep_stages(poppy_cuda_ctx* c, int keep) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    c->keep_stages = keep != 0;
+    return 0;
+}
+
+int poppy_cuda_set_chunk_frames(poppy_cuda_ctx* c, int frames) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (frames < 1) return fail(c, POPPY_CUDA_ERR_INVALID, "chunk frames must be >= 1");
+    c->want_chunk = frames;
+    return 0;
+}
+
+int poppy_cuda_set_stage_timing(poppy_cuda_ctx* c, int enable) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    c->stage_timing = enable != 0;
+    return 0;
+}
+
+int poppy_cuda_set_pair(poppy_cuda_ctx* c, const uint8_t* bgr1, size_t step1, const uint8_t* bgr2, size_t step2,
+                        const float* gabor, size_t gstep) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (!bgr1 || !bgr2 || !gabor) return fail(c, POPPY_CUDA_ERR_INVALID, "null image pointer");
+    const size_t row = (size_t)c->w * 3, grow = row * sizeof(float);
+    if (step1 < row || step2 < row || gstep < grow) return fail(c, POPPY_CUDA_ERR_INVALID, "row stride smaller than a row");
+    CU_TRY(c, cudaSetDevice(c->device));
+    uint8_t* stage = nullptr;
+    float* gstage = nullptr;
+    CU_TRY(c, dmalloc(&stage, c->frame_bytes()));
+    cudaError_t e = dmalloc(&gstage, c->pixels() * 3);
+    if (e != cudaSuccess) { cudaFree(stage); return fail(c, POPPY_CUDA_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    int rc = 0;
+    auto run = [&]() -> int {
+        CU_TRY(c, cudaMemcpy2DAsync(stage, row, bgr1, step1, row, c->h, cudaMemcpyHostToDevice, c->stream));
+        launch_bgr_to_bgrx(c->stream, stage, c->d_src1, c->w, c->h);
+        CU_TRY(c, cudaMemcpy2DAsync(stage, row, bgr2, step2, row, c->h, cudaMemcpyHostToDevice, c->stream));
+        launch_bgr_to_bgrx(c->stream, stage, c->d_src2, c->w, c->h);
+        CU_TRY(c, cudaMemcpy2DAsync(gstage, grow, gabor, gstep, grow, c->h, cudaMemcpyHostToDevice, c->stream));
+        launch_mask_basis(c->stream, gstage, c->d_mbasis, c->w, c->h);
+        c->launches += 3; c->class_launches[KC_MISC] += 3;
+        CU_TRY(c, cudaGetLastError());
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    rc = run();
+    cudaFree(stage);
+    cudaFree(gstage);
+    if (rc == 0) c->have_pair = true;
+    return rc;
+}
+
+int poppy_cuda_set_points(poppy_cuda_ctx* c, const float* pts1, const float* pts2, int n) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (!pts1 || !pts2 || n < 3) return fail(c, POPPY_CUDA_ERR_INVALID, "need two point sets of >= 3 points");
+    if (n > c->max_points) return fail(c, POPPY_CUDA_ERR_CAPACITY, "%d points (max %d)", n, c->max_points);
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaMemcpyAsync(c->d_pts1_raw, pts1, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->d_pts2_raw, pts2, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    launch_clip_points(c->stream, c->d_pts1_raw, c->d_pts1, n, c->w, c->h);
+    launch_clip_points(c->stream, c->d_pts2_raw, c->d_pts2, n, c->w, c->h);
+    c->launches += 2; c->class_launches[KC_MISC] += 2;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaStreamSynchronize(c->stream));   // the host arrays may be pageable and reused by the caller
+    c->n_points = n;
+    c->have_points = true;
+    return 0;
+}
+
+int poppy_cuda_render(poppy_cuda_ctx* c, int n_frames, const float* shape, const double* mask, const int32_t* tri_idx,
+                      const int32_t* tri_off, int chain) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (!c->have_pair || !c->have_points) return fail(c, POPPY_CUDA_ERR_STATE, "set_pair and set_points must precede render");
+    if (!shape || !mask || !tri_idx || !tri_off) return fail(c, POPPY_CUDA_ERR_INVALID, "null argument");
+    if (n_frames < 1 || n_frames > c->max_frames) return fail(c, POPPY_CUDA_ERR_CAPACITY, "%d frames (max %d)", n_frames, c->max_frames);
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (int rc = ensure_chunk(c)) return rc;
+    collect_timing(c);
+    std::fill(c->class_ms, c->class_ms + KC_COUNT, 0.f);
+    std::fill(c->class_launches, c->class_launches + KC_COUNT, 0ull);
+    CU_TRY(c, cudaEventRecord(c->ev_begin, c->stream));
+    const int B = chain ? 1 : c->chunk;
+    int slot = 0;
+    for (int first = 0; first < n_frames; first += B, slot ^= 1) {
+        const int nb = std::min(B, n_frames - first);
+        if (int rc = render_chunk(c, first, nb, shape, mask, tri_idx, tri_off, chain != 0, slot)) return rc;
+    }
+    CU_TRY(c, cudaEventRecord(c->ev_end, c->stream));
+    c->last_frames = n_frames;
+    return 0;
+}
+
+int poppy_cuda_download(poppy_cuda_ctx* c, int first, int count, uint8_t* dst, size_t step, size_t frame_stride) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    const size_t row = (size_t)c->w * 3;
+    if (!dst || first < 0 || count < 1 || first + count > c->max_frames || step < row || frame_stride < step * c->h)
+        return fail(c, POPPY_CUDA_ERR_INVALID, "bad download range or strides");
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (step == row && frame_stride == c->frame_bytes()) {
+        CU_TRY(c, cudaMemcpyAsync(dst, c->d_frames + (size_t)first * c->frame_bytes(), (size_t)count * c->frame_bytes(),
+                                  cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        for (int i = 0; i < count; ++i)
+            CU_TRY(c, cudaMemcpy2DAsync(dst + (size_t)i * frame_stride, step, c->d_frames + (size_t)(first + i) * c->frame_bytes(),
+                                        row, row, c->h, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return 0;
+}
+
+int poppy_cuda_get_morphed_points(poppy_cuda_ctx* c, int frame, float* xy) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (!xy || frame < 0 || frame >= c->last_frames) return fail(c, POPPY_CUDA_ERR_INVALID, "frame %d not rendered", frame);
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaMemcpyAsync(xy, c->d_morphed + (size_t)frame * c->max_points, (size_t)c->n_points * 8,
+                              cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int poppy_cuda_frame_device_ptr(poppy_cuda_ctx* c, int frame, void** dptr, size_t* bytes) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (!dptr || frame < 0 || frame >= c->max_frames) return fail(c, POPPY_CUDA_ERR_INVALID, "bad frame slot");
+    *dptr = c->d_frames + (size_t)frame * c->frame_bytes();
+    if (bytes) *bytes = c->frame_bytes();
+    return 0;
+}
+
+int poppy_cuda_checksum(poppy_cuda_ctx* c, int first, int count, uint64_t* out) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (!out || first < 0 || count < 1 || first + count > c->max_frames) return fail(c, POPPY_CUDA_ERR_INVALID, "bad range");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaMemsetAsync(c->d_sum, 0, 8, c->stream));
+    launch_checksum(c->stream, c->d_frames + (size_t)first * c->frame_bytes(), (size_t)count * c->frame_bytes(), c->d_sum);
+    c->launches++; c->class_launches[KC_MISC]++;
+    unsigned long long v = 0;
+    CU_TRY(c, cudaMemcpyAsync(&v, c->d_sum, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    *out = v;
+    return 0;
+}
+
+int poppy_cuda_sync(poppy_cuda_ctx* c) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int poppy_cuda_get_stream(poppy_cuda_ctx* c, void** stream) {
+    if (!c || !stream) return POPPY_CUDA_ERR_INVALID;
+    *stream = (void*)c->stream;
+    return 0;
+}
+
+int poppy_cuda_last_render_ms(poppy_cuda_ctx* c, float* ms) {
+    if (!c || !ms) return POPPY_CUDA_ERR_INVALID;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaEventSynchronize(c->ev_end));
+    CU_TRY(c, cudaEventElapsedTime(ms, c->ev_begin, c->ev_end));
+    return 0;
+}
+
+int poppy_cuda_launch_count(poppy_cuda_ctx* c, uint64_t* launches) {
+    if (!c || !launches) return POPPY_CUDA_ERR_INVALID;
+    *launches = c->launches;
+    return 0;
+}
+
+int poppy_cuda_stage_times(poppy_cuda_ctx* c, const char** names, float* ms, uint64_t* launches, int cap) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    collect_timing(c);
+    for (int i = 0; i < KC_COUNT && i < cap; ++i) {
+        if (names) names[i] = kClassNames[i];
+        if (ms) ms[i] = c->class_ms[i];
+        if (launches) launches[i] = c->class_launches[i];
+    }
+    return KC_COUNT;
+}
+
+int poppy_cuda_debug_read(poppy_cuda_ctx* c, int stage, int frame, void* dst, size_t bytes) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (!dst) return fail(c, POPPY_CUDA_ERR_INVALID, "dst is null");
+    if (!c->keep_stages || c->chunk != 1) return fail(c, POPPY_CUDA_ERR_STATE, "stage buffers need set_keep_stages(1) before render");
+    if (frame != c->last_frames - 1 && stage != POPPY_STAGE_MORPHED_POINTS)
+        return fail(c, POPPY_CUDA_ERR_STATE, "only the last rendered frame's stage buffers are resident");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    const size_t px = c->pixels();
+    const int w = c->w, h = c->h;
+    FrameParams P;
+    CU_TRY(c, cudaMemcpy(&P, c->d_fp, sizeof P, cudaMemcpyDeviceToHost));
+    auto need = [&](size_t want) -> int {
+        return bytes == want ? 0 : fail(c, POPPY_CUDA_ERR_INVALID, "stage %d holds %zu bytes, caller gave %zu", stage, want, bytes);
+    };
+    switch (stage) {
+    case POPPY_STAGE_MORPHED_POINTS:
+        if (frame < 0 || frame >= c->last_frames) return fail(c, POPPY_CUDA_ERR_INVALID, "frame not rendered");
+        if (int rc = need((size_t)c->n_points * 8)) return rc;
+        CU_TRY(c, cudaMemcpy(dst, c->d_morphed + (size_t)frame * c->max_points, bytes, cudaMemcpyDeviceToHost));
+        return 0;
+    case POPPY_STAGE_TRI_MAP:
+        if (int rc = need(px * 4)) return rc;
+        CU_TRY(c, cudaMemcpy(dst, c->d_trimap, bytes, cudaMemcpyDeviceToHost));
+        return 0;
+    case POPPY_STAGE_INV_M1:
+    case POPPY_STAGE_INV_M2: {
+        if (int rc = need((size_t)P.n_tri * 36)) return rc;
+        std::vector<TriInverse> tmp(std::max(P.n_tri, 1));
+        CU_TRY(c, cudaMemcpy(tmp.data(), c->d_inv, (size_t)P.n_tri * sizeof(TriInverse), cudaMemcpyDeviceToHost));
+        float* o = (float*)dst;
+        for (int i = 0; i < P.n_tri; ++i) std::memcpy(o + 9 * i, stage == POPPY_STAGE_INV_M1 ? tmp[i].a : tmp[i].b, 36);
+        return 0;
+    }
+    case POPPY_STAGE_WARPED1:
+    case POPPY_STAGE_WARPED2: {
+        if (int rc = need(px * 3)) return rc;
+        std::vector<uint2> tmp(px);
+        CU_TRY(c, cudaMemcpy(tmp.data(), c->d_warped, px * 8, cudaMemcpyDeviceToHost));
+        uint8_t* o = (uint8_t*)dst;
+        for (size_t i = 0; i < px; ++i) {
+            uint32_t v = stage == POPPY_STAGE_WARPED1 ? tmp[i].x : tmp[i].y;
+            o[3 * i] = v & 255; o[3 * i + 1] = (v >> 8) & 255; o[3 * i + 2] = (v >> 16) & 255;
+        }
+        return 0;
+    }
+    case POPPY_STAGE_MASK:
+        if (int rc = need(px * 4)) return rc;
+        CU_TRY(c, cudaMemcpy(dst, c->d_mask0, bytes, cudaMemcpyDeviceToHost));
+        return 0;
+    case POPPY_STAGE_LAP_BLEND: {
+        if (int rc = need(px * 12)) return rc;
+        const LevelDesc& d = c->lv[0];
+        std::vector<float> tmp(3 * d.plane_stride);
+        CU_TRY(c, cudaMemcpy(tmp.data(), o_level(c, 0), tmp.size() * 4, cudaMemcpyDeviceToHost));
+        float* o = (float*)dst;
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x)
+                for (int ch = 0; ch < 3; ++ch) o[((size_t)y * w + x) * 3 + ch] = tmp[ch * d.plane_stride + (size_t)y * d.pitch + x];
+        return 0;
+    }
+    default:
+        return fail(c, POPPY_CUDA_ERR_INVALID, "unknown stage %d", stage);
+    }
+}
+
+}  // extern "C"
