@@ -59,6 +59,10 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
                       int max_triangles, int max_batch_frames);
 void poppy_cuda_destroy(poppy_cuda_ctx* ctx);
 
+/* Geometry and capacities the context was created with (any pointer may be NULL). */
+int poppy_cuda_get_info(const poppy_cuda_ctx* ctx, int* width, int* height, int* pyramid_levels, int* max_points,
+                        int* max_triangles, int* max_batch_frames);
+
 /* Options; call before the first render. */
 int poppy_cuda_set_keep_stages(poppy_cuda_ctx* ctx, int keep);       /* 1: chunk size 1, stage buffers readable */
 int poppy_cuda_set_chunk_frames(poppy_cuda_ctx* ctx, int frames);    /* frames rendered per kernel batch (>=1) */

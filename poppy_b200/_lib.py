@@ -33,7 +33,19 @@ def load():
         "poppy_cuda_device_count": (i32, []),
         "poppy_cuda_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, i32, i32]),
         "poppy_cuda_destroy": (None, [vp]),
+        "poppy_cuda_get_info": (i32, [vp] + [C.POINTER(i32)] * 6),
         "poppy_cuda_set_keep_stages": (i32, [vp, i32]),
+        # host stages (include/poppy_host.h)
+        "poppy_host_morph_points": (i32, [vp, vp, i32, C.c_double, i32, i32, vp]),
+        "poppy_host_triangulate": (i32, [vp, i32, i32, i32, vp, i32, C.POINTER(i32)]),
+        "poppy_host_chain_ratio": (C.c_double, [i32, i32]),
+        "poppy_host_plan_create": (i32, [C.POINTER(vp), vp, vp, i32, i32, i32, i32, vp, i32, i32]),
+        "poppy_host_plan_triangles": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]),
+        "poppy_host_plan_points": (i32, [vp, i32, C.POINTER(vp)]),
+        "poppy_host_plan_destroy": (None, [vp]),
+        "poppy_morph_images": (i32, [vp, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, vp, vp, i32, C.c_double,
+                               C.c_double, vp, C.c_size_t, vp]),
+        "poppy_host_last_error": (C.c_char_p, []),
         "poppy_cuda_set_chunk_frames": (i32, [vp, i32]),
         "poppy_cuda_set_stage_timing": (i32, [vp, i32]),
         "poppy_cuda_set_pair": (i32, [vp, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t]),
@@ -67,5 +79,10 @@ CUDA_ABI_SYMBOLS = [
     "poppy_cuda_render", "poppy_cuda_download", "poppy_cuda_get_morphed_points", "poppy_cuda_frame_device_ptr",
     "poppy_cuda_checksum", "poppy_cuda_sync", "poppy_cuda_get_stream", "poppy_cuda_last_render_ms",
     "poppy_cuda_launch_count", "poppy_cuda_stage_times", "poppy_cuda_debug_read", "poppy_cuda_last_error",
-    "poppy_cuda_version",
+    "poppy_cuda_version", "poppy_cuda_get_info",
+]
+HOST_ABI_SYMBOLS = [
+    "poppy_host_morph_points", "poppy_host_triangulate", "poppy_host_chain_ratio", "poppy_host_plan_create",
+    "poppy_host_plan_triangles", "poppy_host_plan_points", "poppy_host_plan_destroy", "poppy_morph_images",
+    "poppy_host_last_error",
 ]

@@ -1,0 +1,84 @@
+// Host topology stage: incremental Delaunay triangulation of the morphed points with the exact insertion,
+// point-location and enumeration behaviour of cv::Subdiv2D 4.6.0, because the *order* of the triangle list decides
+// which triangle owns a shared pixel (reference src/algo.cpp:60-81,95-106,205-213).
+//
+// Restated from the published quad-edge algorithm (Guibas & Stolfi 1985) as OpenCV instantiates it:
+//   OCV imgproc/src/subdivision2d.cpp:45-110 (edge algebra), :222-248 (splice / connect / swap), :264-404 (locate),
+//   :412-490 (insert), :492-540 (bounding triangle), :756-785 (getTriangleList).
+// The topology stays on the host by design (north-star); this file replaces only the O(T*N) std::find lookup of
+// get_triangle_indices by an O(1) table that returns the same first-occurrence index.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace poppy {
+
+struct Point2f {
+    float x, y;
+};
+
+// clip_points(), reference src/util.cpp:453-460 (note: ">" — a coordinate equal to cols/rows passes)
+void clip_points(std::vector<Point2f>& pts, int cols, int rows);
+
+// make_uniq(), reference src/util.cpp:541-548: first occurrences in order. first_index[i] is the position in
+// `pts` of unique point i.
+void make_uniq(const std::vector<Point2f>& pts, std::vector<Point2f>& out, std::vector<int32_t>* first_index = nullptr);
+
+class DelaunayMesh {
+public:
+    // bounding rect [0,w) x [0,h), as Subdiv2D(Rect(0,0,w,h))
+    DelaunayMesh(int width, int height);
+
+    // Subdiv2D::insert. Returns the vertex id (>= 4 for real points) or -1 when the point is outside the rect
+    // (where cv::Subdiv2D throws StsOutOfRange); error() then describes it.
+    int insert(Point2f pt);
+
+    // Subdiv2D::getTriangleList order; each triangle as three vertex ids (all >= 4).
+    void triangles(std::vector<int32_t>& vertex_ids) const;
+
+    Point2f vertex(int id) const { return pt_[id]; }
+    int vertex_count() const { return (int)pt_.size(); }
+    const std::string& error() const { return err_; }
+
+private:
+    // edge id = 4 * quad + rot
+    int onext(int e) const { return next_[e]; }
+    static int rot(int e, int r) { return (e & ~3) + ((e + r) & 3); }
+    static int sym(int e) { return e ^ 2; }
+    int oprev(int e) const { return rot(next_[rot(e, 1)], 1); }
+    int lnext(int e) const { return rot(next_[rot(e, 3)], 1); }
+    int lprev(int e) const { return sym(next_[e]); }
+    int dprev(int e) const { return rot(next_[rot(e, 3)], 3); }
+    int org(int e) const { return org_[e]; }
+    int dst(int e) const { return org_[sym(e)]; }
+
+    int new_quad();
+    void free_quad_of(int e);
+    int new_vertex(Point2f p);
+    void splice(int a, int b);
+    void set_ends(int e, int o, int d);
+    int connect(int a, int b);
+    void flip(int e);
+    int side_of(Point2f p, int e) const;      // sign of "p is right of e"
+    enum Where { kError = -2, kOutside = -1, kInside = 0, kVertex = 1, kOnEdge = 2 };
+    Where locate(Point2f p, int& edge, int& vertex);
+
+    std::vector<int> next_;     // 4 per quad-edge
+    std::vector<int> org_;      // 4 per quad-edge (origin vertex of each of the 4 directed edges; odd slots unused)
+    std::vector<Point2f> pt_;
+    std::vector<int> first_edge_;
+    int free_quad_ = 0;
+    int recent_ = 0;
+    Point2f top_left_{0, 0}, bottom_right_{0, 0};
+    std::string err_;
+};
+
+// The host stage of morph_images for one frame (reference src/algo.cpp:205-213): clip, dedupe, triangulate, and
+// return triangle vertex indices into `points` (first exact-equal occurrence), in getTriangleList order.
+// Returns false (with `error`) where the reference would throw.
+bool triangulate_points(std::vector<Point2f> points, int width, int height, std::vector<int32_t>& tri_idx,
+                        std::string* error = nullptr);
+
+}  // namespace poppy

@@ -1,0 +1,180 @@
+// extern "C" layer of the host stages (include/poppy_host.h).
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/poppy_host.h"
+#include "delaunay.hpp"
+#include "morph_images.hpp"
+
+using poppy::Point2f;
+
+namespace {
+thread_local std::string g_host_error;
+
+int host_fail(int code, const std::string& msg) {
+    g_host_error = msg;
+    return code;
+}
+
+// morph_points(), reference src/algo.cpp:50-58: the first product is double, the second float x float, the sum double
+float lerp_coord(float a, float b, float s) {
+    float sb = s * b;
+    return (float)((1.0 - (double)s) * (double)a + (double)sb);
+}
+
+void lerp_points(const std::vector<Point2f>& a, const std::vector<Point2f>& b, float s, int w, int h,
+                 std::vector<Point2f>& out) {
+    out.resize(a.size());
+    for (size_t i = 0; i < a.size(); ++i) out[i] = {lerp_coord(a[i].x, b[i].x, s), lerp_coord(a[i].y, b[i].y, s)};
+    poppy::clip_points(out, w, h);
+}
+
+std::vector<Point2f> to_points(const float* xy, int n) {
+    std::vector<Point2f> v(n);
+    if (n) std::memcpy(v.data(), xy, (size_t)n * sizeof(Point2f));
+    return v;
+}
+}  // namespace
+
+struct poppy_host_plan {
+    int n = 0, frames = 0, max_tri = 0;
+    std::vector<std::vector<Point2f>> points;    // per frame
+    std::vector<int32_t> tri;                    // concatenated
+    std::vector<int32_t> offsets;                // frames + 1
+};
+
+extern "C" {
+
+const char* poppy_host_last_error(void) { return g_host_error.c_str(); }
+
+int poppy_host_morph_points(const float* p1, const float* p2, int n, double shape_ratio, int w, int h, float* out) {
+    if (!p1 || !p2 || !out || n < 0) return host_fail(POPPY_CUDA_ERR_INVALID, "null argument");
+    std::vector<Point2f> a = to_points(p1, n), b = to_points(p2, n), m;
+    poppy::clip_points(a, w, h);
+    poppy::clip_points(b, w, h);
+    lerp_points(a, b, (float)shape_ratio, w, h, m);
+    if (n) std::memcpy(out, m.data(), (size_t)n * sizeof(Point2f));
+    return 0;
+}
+
+int poppy_host_triangulate(const float* pts, int n, int w, int h, int32_t* tri_idx, int cap, int* n_tri) {
+    if (!pts || !n_tri || n < 0) return host_fail(POPPY_CUDA_ERR_INVALID, "null argument");
+    std::vector<int32_t> tri;
+    std::string err;
+    if (!poppy::triangulate_points(to_points(pts, n), w, h, tri, &err)) return host_fail(POPPY_CUDA_ERR_INVALID, err);
+    *n_tri = (int)tri.size() / 3;
+    if (*n_tri > cap) return host_fail(POPPY_CUDA_ERR_CAPACITY, "triangle buffer too small");
+    if (tri_idx && !tri.empty()) std::memcpy(tri_idx, tri.data(), tri.size() * sizeof(int32_t));
+    return 0;
+}
+
+double poppy_host_chain_ratio(int j, int n_frames) {
+    // linear = j / N; progress = 0 for linear == 0, 1 for linear == 1, else (1 / (1 - linear)) / N; capped at 1
+    const double N = (double)n_frames;
+    const double linear = j / N;
+    double progress;
+    if (linear == 0) progress = 0;
+    else if (linear == 1) progress = 1;
+    else progress = (1.0 / (1.0 - linear)) / N;
+    return progress > 1 ? 1 : progress;
+}
+
+int poppy_host_plan_create(poppy_host_plan** out, const float* p1, const float* p2, int n, int w, int h, int n_frames,
+                           const float* shape_ratio, int chain, int threads) {
+    if (!out) return host_fail(POPPY_CUDA_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!p1 || !p2 || !shape_ratio || n < 3 || n_frames < 1) return host_fail(POPPY_CUDA_ERR_INVALID, "bad argument");
+    poppy_host_plan* plan = new poppy_host_plan();
+    plan->n = n;
+    plan->frames = n_frames;
+    plan->points.resize(n_frames);
+    std::vector<Point2f> a = to_points(p1, n), b = to_points(p2, n);
+    poppy::clip_points(a, w, h);
+    poppy::clip_points(b, w, h);
+    // points first: in chain mode frame f starts from frame f-1's morphed points (src/poppy.hpp:178-179); this
+    // recurrence involves no pixels, so it is planned ahead of the render
+    for (int f = 0; f < n_frames; ++f)
+        lerp_points(chain && f > 0 ? plan->points[f - 1] : a, b, shape_ratio[f], w, h, plan->points[f]);
+    // triangulations are independent: fan out over host threads
+    std::vector<std::vector<int32_t>> tris(n_frames);
+    std::vector<std::string> errs(n_frames);
+    std::atomic<int> next{0}, failed{-1};
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, n_frames));
+    auto work = [&] {
+        for (int f; (f = next.fetch_add(1)) < n_frames;)
+            if (!poppy::triangulate_points(plan->points[f], w, h, tris[f], &errs[f])) {
+                int expected = -1;
+                failed.compare_exchange_strong(expected, f);
+            }
+    };
+    std::vector<std::thread> pool;
+    for (int i = 1; i < nt; ++i) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (failed.load() >= 0) {
+        std::string msg = "frame " + std::to_string(failed.load()) + ": " + errs[failed.load()];
+        delete plan;
+        return host_fail(POPPY_CUDA_ERR_INVALID, msg);
+    }
+    plan->offsets.assign(n_frames + 1, 0);
+    for (int f = 0; f < n_frames; ++f) {
+        const int t = (int)tris[f].size() / 3;
+        plan->offsets[f + 1] = plan->offsets[f] + t;
+        plan->max_tri = std::max(plan->max_tri, t);
+    }
+    plan->tri.reserve((size_t)plan->offsets[n_frames] * 3);
+    for (int f = 0; f < n_frames; ++f) plan->tri.insert(plan->tri.end(), tris[f].begin(), tris[f].end());
+    *out = plan;
+    return 0;
+}
+
+int poppy_host_plan_triangles(const poppy_host_plan* plan, const int32_t** tri_idx, const int32_t** tri_offsets,
+                              int* max_triangles) {
+    if (!plan) return host_fail(POPPY_CUDA_ERR_INVALID, "plan is null");
+    if (tri_idx) *tri_idx = plan->tri.data();
+    if (tri_offsets) *tri_offsets = plan->offsets.data();
+    if (max_triangles) *max_triangles = plan->max_tri;
+    return 0;
+}
+
+int poppy_host_plan_points(const poppy_host_plan* plan, int frame, const float** xy) {
+    if (!plan || !xy || frame < 0 || frame >= plan->frames) return host_fail(POPPY_CUDA_ERR_INVALID, "bad frame");
+    *xy = &plan->points[frame][0].x;
+    return 0;
+}
+
+void poppy_host_plan_destroy(poppy_host_plan* plan) { delete plan; }
+
+int poppy_morph_images(poppy_cuda_ctx* ctx, const uint8_t* c1, size_t step1, const uint8_t* c2, size_t step2,
+                       const float* gabor2, size_t gstep, const float* sp1, const float* sp2, int n,
+                       double shape_ratio, double mask_ratio, uint8_t* dst, size_t dst_step, float* morphed_xy) {
+    if (!ctx || !c1 || !c2 || !gabor2 || !sp1 || !sp2 || !dst) return host_fail(POPPY_CUDA_ERR_INVALID, "null argument");
+    int w = 0, h = 0, max_tri = 0;
+    if (int rc = poppy_cuda_get_info(ctx, &w, &h, nullptr, nullptr, &max_tri, nullptr)) return host_fail(rc, "bad context");
+    // host stages, reference src/algo.cpp:184-213
+    std::vector<Point2f> a = to_points(sp1, n), b = to_points(sp2, n), m;
+    poppy::clip_points(a, w, h);
+    poppy::clip_points(b, w, h);
+    const float s = (float)shape_ratio;
+    lerp_points(a, b, s, w, h, m);
+    std::vector<int32_t> tri;
+    std::string err;
+    if (!poppy::triangulate_points(m, w, h, tri, &err)) return host_fail(POPPY_CUDA_ERR_INVALID, err);
+    const int32_t offs[2] = {0, (int32_t)(tri.size() / 3)};
+    int rc;
+    if ((rc = poppy_cuda_set_pair(ctx, c1, step1, c2, step2, gabor2, gstep)) != 0 ||
+        (rc = poppy_cuda_set_points(ctx, sp1, sp2, n)) != 0 ||
+        (rc = poppy_cuda_render(ctx, 1, &s, &mask_ratio, tri.data(), offs, 0)) != 0 ||
+        (rc = poppy_cuda_download(ctx, 0, 1, dst, dst_step, dst_step * (size_t)h)) != 0 ||
+        (morphed_xy && (rc = poppy_cuda_get_morphed_points(ctx, 0, morphed_xy)) != 0) ||
+        (rc = poppy_cuda_sync(ctx)) != 0)
+        return host_fail(rc, poppy_cuda_last_error(ctx));
+    return 0;
+}
+
+}  // extern "C"

@@ -341,6 +341,18 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
     delete c;
 }
 
+int poppy_cuda_get_info(const poppy_cuda_ctx* c, int* width, int* height, int* pyramid_levels, int* max_points,
+                        int* max_triangles, int* max_batch_frames) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (width) *width = c->w;
+    if (height) *height = c->h;
+    if (pyramid_levels) *pyramid_levels = c->levels;
+    if (max_points) *max_points = c->max_points;
+    if (max_triangles) *max_triangles = c->max_tri;
+    if (max_batch_frames) *max_batch_frames = c->max_frames;
+    return 0;
+}
+
 int poppy_cuda_set_keep_stages(poppy_cuda_ctx* c, int keep) {
     if (!c) return POPPY_CUDA_ERR_INVALID;
     c->keep_stages = keep != 0;
