@@ -393,20 +393,33 @@ const uint32_t kGauss9Bits[5] = {0x3ecc4252u, 0x3e77c75du, 0x3d5d25cdu, 0x3b9139
 float gauss_tap(int k) { float f; std::memcpy(&f, &kGauss9Bits[std::abs(k)], 4); return f; }
 
 Img gaussian9(const Img& s) {
+    // Both filters run 8 floats at a time as FMA chains; the last (w*cn) % 8 elements of every row fall to the
+    // generic scalar loops (filter.simd.hpp:2477-2487, 2753-2759), which the reference build does not contract:
+    // there each product and each sum is rounded separately (established against the reference library).
     Img t(s.w, s.h, s.c), o(s.w, s.h, s.c);
+    const int n = s.w * s.c, tail_from = n - n % 8;
     for (int y = 0; y < s.h; ++y)
         for (int x = 0; x < s.w; ++x)
             for (int c = 0; c < s.c; ++c) {
+                const bool fused = x * s.c + c < tail_from;
+                if (s.w == 1) { t.at(x, y, c) = s.at(x, y, c); continue; }   // 1-pixel-wide: kernel shrinks to [1]
                 float acc = gauss_tap(-4) * s.at(reflect101(x - 4, s.w), y, c);
-                for (int k = -3; k <= 4; ++k) acc = std::fmaf(s.at(reflect101(x + k, s.w), y, c), gauss_tap(k), acc);
+                for (int k = -3; k <= 4; ++k) {
+                    float v = s.at(reflect101(x + k, s.w), y, c);
+                    acc = fused ? std::fmaf(v, gauss_tap(k), acc) : acc + gauss_tap(k) * v;
+                }
                 t.at(x, y, c) = acc;
             }
     for (int y = 0; y < s.h; ++y)
         for (int x = 0; x < s.w; ++x)
             for (int c = 0; c < s.c; ++c) {
-                float acc = std::fmaf(gauss_tap(0), t.at(x, y, c), 0.f);
-                for (int k = 1; k <= 4; ++k)
-                    acc = std::fmaf(gauss_tap(k), t.at(x, reflect101(y + k, s.h), c) + t.at(x, reflect101(y - k, s.h), c), acc);
+                const bool fused = x * s.c + c < tail_from;
+                if (s.h == 1) { o.at(x, y, c) = t.at(x, y, c); continue; }   // smooth.dispatch.cpp:621-628
+                float acc = fused ? std::fmaf(gauss_tap(0), t.at(x, y, c), 0.f) : gauss_tap(0) * t.at(x, y, c) + 0.f;
+                for (int k = 1; k <= 4; ++k) {
+                    float pair = t.at(x, reflect101(y + k, s.h), c) + t.at(x, reflect101(y - k, s.h), c);
+                    acc = fused ? std::fmaf(gauss_tap(k), pair, acc) : acc + gauss_tap(k) * pair;
+                }
                 o.at(x, y, c) = acc;
             }
     return o;

@@ -4,7 +4,10 @@
 //   GaussianBlur(sigma 1) -> 9 taps, separable, BORDER_REFLECT_101. Row filter and symmetric column filter both
 //   run as FMA chains in OpenCV's FMA-dispatched translation unit:
 //     row:    s = k[-4]*x[-4]; s = fma(x[j], k[j], s), j = -3..4       (OCV imgproc/src/filter.simd.hpp:1663-1681,2477-2487)
-//     column: s = fma(k0, t0, 0); s = fma(k[j], t[+j] + t[-j], s), j = 1..4   (filter.simd.hpp:1909-1960,2753-2759)
+//     column: s = fma(k0, t0, 0); s = fma(k[j], t[+j] + t[-j], s), j = 1..4   (filter.simd.hpp:1909-1960)
+//   except for the last (3*w) % 8 interleaved elements of every row, which fall to the generic scalar loops
+//   (filter.simd.hpp:2477-2487, 2753-2759); the reference build does not contract those: products and sums are
+//   rounded separately there.
 //   diff = x - blur; 3x3 per-channel median with replicated border (median_blur.simd.hpp:677-745);
 //   where ||diff||_2 >= 0.3 (cv::norm of a Vec3f: double accumulation + sqrt): x + amount*diff, else x
 //   (src/util.cpp:135-145, unfused); then cvRound(v*255) saturated to 8 bits (convert_scale.simd.hpp, saturate.hpp:105).
@@ -56,6 +59,7 @@ k_unsharp_store(const float* __restrict__ lap, int w, int h, int pitch, size_t s
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH, f = blockIdx.z;
     const int tid = threadIdx.x;
     const float* img = lap + (size_t)f * 3 * stride;
+    const int tail_from = 3 * w - (3 * w) % 8;      // first interleaved element handled by the scalar filter loops
 
     // 1) row pass for every cell of the halo'd tile
     for (int i = tid; i < TR * CW; i += 256) {
@@ -70,8 +74,15 @@ k_unsharp_store(const float* __restrict__ lap, int w, int h, int pitch, size_t s
         for (int c = 0; c < 3; ++c) {
             const float* row = img + (size_t)c * stride + (size_t)ry * pitch;
             float s = __fmul_rn(gk(-4), __ldg(row + cx[0]));
+            if (w == 1) {
+                s = __ldg(row);          // GaussianBlur shrinks the kernel to [1] along a 1-pixel axis
+            } else if (3 * gx + c < tail_from) {
 #pragma unroll
-            for (int j = 1; j < 9; ++j) s = fmaf(__ldg(row + cx[j]), gk(j - 4), s);
+                for (int j = 1; j < 9; ++j) s = fmaf(__ldg(row + cx[j]), gk(j - 4), s);
+            } else {
+#pragma unroll
+                for (int j = 1; j < 9; ++j) s = __fadd_rn(s, __fmul_rn(gk(j - 4), __ldg(row + cx[j])));
+            }
             s_row[rj][c][ci] = s;
         }
     }
@@ -88,9 +99,19 @@ k_unsharp_store(const float* __restrict__ lap, int w, int h, int pitch, size_t s
         for (int j = 1; j <= 4; ++j) { rp[j] = reflect101(gy + j, h) - base; rm[j] = reflect101(gy - j, h) - base; }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float s = fmaf(gk(0), s_row[gy - base][c][ci], 0.f);
+            float s;
+            if (h == 1) {
+                s = s_row[gy - base][c][ci];
+            } else if (3 * gx + c < tail_from) {
+                s = fmaf(gk(0), s_row[gy - base][c][ci], 0.f);
 #pragma unroll
-            for (int j = 1; j <= 4; ++j) s = fmaf(gk(j), __fadd_rn(s_row[rp[j]][c][ci], s_row[rm[j]][c][ci]), s);
+                for (int j = 1; j <= 4; ++j) s = fmaf(gk(j), __fadd_rn(s_row[rp[j]][c][ci], s_row[rm[j]][c][ci]), s);
+            } else {
+                s = __fadd_rn(__fmul_rn(gk(0), s_row[gy - base][c][ci]), 0.f);
+#pragma unroll
+                for (int j = 1; j <= 4; ++j)
+                    s = __fadd_rn(s, __fmul_rn(gk(j), __fadd_rn(s_row[rp[j]][c][ci], s_row[rm[j]][c][ci])));
+            }
             const float x = __ldg(img + (size_t)c * stride + (size_t)gy * pitch + gx);
             s_diff[dj][c][ci] = __fsub_rn(x, s);
         }

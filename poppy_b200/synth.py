@@ -84,3 +84,53 @@ WORKLOADS = {
 def workload_inputs(name: str) -> MorphInputs:
     c = WORKLOADS[name]
     return make_inputs(c["w"], c["h"], c["n_points"], c["jitter"], c["seed"])
+
+
+def shape_image(w: int, h: int, kind: str, seed: int = 0) -> np.ndarray:
+    """Hard-edged synthetic picture (a filled square or disc on a flat background, mild noise) — the analogue of
+    the reference's square.png / circle.png demo pair; sharp edges drive the unsharp-mask threshold branch."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    yy, xx = np.mgrid[0:h, 0:w]
+    cx, cy, r = w / 2.0, h / 2.0, min(w, h) * 0.3
+    if kind == "square":
+        inside = (np.abs(xx - cx) <= r) & (np.abs(yy - cy) <= r)
+        fg, bg = (30, 40, 220), (235, 235, 235)
+    else:
+        inside = (xx - cx) ** 2 + (yy - cy) ** 2 <= r * r
+        fg, bg = (220, 60, 30), (20, 20, 20)
+    img = np.where(inside[..., None], np.array(fg, np.float32), np.array(bg, np.float32))
+    img += rng.normal(0, 2.0, size=img.shape).astype(np.float32)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def shape_inputs(w: int, h: int, n_points: int = 40, seed: int = 11) -> MorphInputs:
+    """square -> disc pair with points on the two outlines (matched by angle) plus random interior points."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cx, cy, r = w / 2.0, h / 2.0, min(w, h) * 0.3
+    ang = np.linspace(0, 2 * np.pi, n_points, endpoint=False)
+    circ = np.stack([cx + r * np.cos(ang), cy + r * np.sin(ang)], 1)
+    t = np.maximum(np.abs(np.cos(ang)), np.abs(np.sin(ang)))
+    sq = np.stack([cx + r * np.cos(ang) / t, cy + r * np.sin(ang) / t], 1)
+    extra = np.stack([rng.uniform(1, w - 2, n_points // 2), rng.uniform(1, h - 2, n_points // 2)], 1)
+    corners = np.array([[0, 0], [w - 1, 0], [0, h - 1], [w - 1, h - 1]], np.float32)
+    p1 = np.concatenate([sq, extra, corners]).astype(np.float32)
+    p2 = np.concatenate([circ, extra + rng.uniform(-3, 3, extra.shape), corners]).astype(np.float32)
+    p2[:, 0] = np.clip(p2[:, 0], 0, w - 1)
+    p2[:, 1] = np.clip(p2[:, 1], 0, h - 1)
+    return MorphInputs(bgr1=shape_image(w, h, "square", seed), bgr2=shape_image(w, h, "disc", seed + 1),
+                       gabor2=smooth_field(w, h, seed + 2, sigma=4.0), pts1=p1, pts2=p2)
+
+
+def block_inputs(w: int, h: int, n_points: int = 30, block: int = 5, seed: int = 51, jitter: float = 2.0) -> MorphInputs:
+    """Random saturated colour blocks: after the pyramid blend many pixels differ from their Gaussian blur by more
+    than the unsharp threshold, so the sharpening branch of unsharp_mask (src/util.cpp:135-145) is exercised."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+
+    def blocks(s):
+        r = np.random.Generator(np.random.PCG64(s))
+        small = r.integers(0, 2, size=((h + block - 1) // block, (w + block - 1) // block, 3), dtype=np.uint8) * 255
+        return np.ascontiguousarray(np.kron(small, np.ones((block, block, 1), np.uint8))[:h, :w])
+
+    pts1, pts2 = matched_points(w, h, n_points, jitter, seed + 3)
+    g = rng.random(size=(h, w, 3), dtype=np.float32)
+    return MorphInputs(bgr1=blocks(seed), bgr2=blocks(seed + 1), gabor2=g, pts1=pts1, pts2=pts2)
