@@ -1,0 +1,165 @@
+"""GPU parity through the public API (Python mirror of the reference interface -> C ABI -> CUDA kernels):
+single frames, the chain recurrence, batched independent phases, the golden fixtures and error behaviour."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from poppy_b200 import api, host, synth
+from tests.util import assert_frame_parity, bits_differ, flat_tri
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(autouse=True)
+def _fresh_api(native_lib):
+    yield
+    api.release()
+
+
+def _ref():
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("reference library not shipped")
+    return ref
+
+
+@pytest.mark.parametrize("kind,w,h,n,s,m,levels", [
+    ("noise", 320, 240, 150, 0.3, 0.3, 6), ("noise", 501, 333, 90, 0.75, 0.2, 64), ("shapes", 256, 256, 48, 0.5, 0.5, 64),
+    ("blocks", 640, 480, 120, 0.1, 0.1, 6), ("blocks", 203, 157, 40, 0.9, 0.95, 3), ("noise", 31, 23, 6, 0.5, 0.5, 8),
+])
+def test_morph_images_matches_reference(kind, w, h, n, s, m, levels):
+    ref = _ref()
+    inp = {"noise": lambda: synth.make_inputs(w, h, n, 8.0, seed=3), "shapes": lambda: synth.shape_inputs(w, h, n, seed=4),
+           "blocks": lambda: synth.block_inputs(w, h, n, seed=5)}[kind]()
+    api.Settings.instance().pyramid_levels = levels
+    dst, mp = api.morph_images(inp.bgr1, inp.bgr2, inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, s, m)
+    want, want_pts = ref.morph_images(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, s, m, levels)
+    assert bits_differ(mp, want_pts) == 0
+    assert_frame_parity(dst, want, (kind, w, h))            # the north-star tolerance ...
+    assert bits_differ(dst, want) == 0                      # ... and in fact bit-identical
+
+
+def test_c_flavour_morph_images(native_lib):
+    ref = _ref()
+    w, h, levels = 200, 160, 5
+    inp = synth.make_inputs(w, h, 70, 6.0, seed=8)
+    from poppy_b200.renderer import MorphRenderer
+    with MorphRenderer(w, h, levels, 128, 512, 1) as r:
+        dst = np.zeros((h, w + 7, 3), np.uint8)             # padded destination rows
+        mp = np.zeros((len(inp.pts1), 2), np.float32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = native_lib.poppy_morph_images(r._ctx, p(inp.bgr1), w * 3, p(inp.bgr2), w * 3, p(inp.gabor2), w * 12,
+                                           p(inp.pts1), p(inp.pts2), len(inp.pts1), 0.6, 0.4, p(dst), (w + 7) * 3, p(mp))
+        assert rc == 0, native_lib.poppy_host_last_error()
+    want, want_pts = ref.morph_images(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, 0.6, 0.4, levels)
+    assert bits_differ(dst[:, :w], want) == 0 and bits_differ(mp, want_pts) == 0
+
+
+def test_chain_sequence_matches_golden():
+    g = np.load(os.path.join(GOLDEN, "chain_shapes_80x64_N12_L64.npz"))
+    api.Settings.instance().pyramid_levels = int(g["levels"])
+    frames = api.morph_sequence(g["bgr1"], g["bgr2"], g["gabor2"], g["pts1"], g["pts2"], number_of_frames=int(g["n_frames"]))
+    for j in range(len(frames)):
+        assert bits_differ(frames[j], g["frames"][j]) == 0, f"chain frame {j}"
+
+
+def test_chain_sequence_matches_reference_live():
+    ref = _ref()
+    w, h, n_frames, levels = 240, 180, 20, 6
+    inp = synth.shape_inputs(w, h, 40, seed=12)
+    api.Settings.instance().pyramid_levels = levels
+
+    class Sink:
+        def __init__(self):
+            self.n = 0
+
+        def write(self, frame):
+            self.n += 1
+
+    sink = Sink()
+    frames = api.morph_sequence(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, writer=sink, number_of_frames=n_frames)
+    want, _ = ref.chain(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, n_frames, levels)
+    assert sink.n == n_frames
+    for j in range(n_frames):
+        assert_frame_parity(frames[j], want[j], f"chain frame {j}")
+        assert bits_differ(frames[j], want[j]) == 0, f"chain frame {j}"
+
+
+@pytest.mark.parametrize("chunk", [1, 3, 16])
+def test_batched_phases_match_reference_for_any_chunking(chunk):
+    ref = _ref()
+    from poppy_b200.renderer import MorphRenderer
+    w, h, levels = 330, 250, 6
+    inp = synth.make_inputs(w, h, 120, 8.0, seed=15)
+    phases = np.linspace(0, 1, 11).astype(np.float32)
+    plan = host.SequencePlan(inp.pts1, inp.pts2, w, h, phases)
+    with MorphRenderer(w, h, levels, len(inp.pts1), plan.max_triangles, len(phases), chunk_frames=chunk) as r:
+        r.set_pair(inp.bgr1, inp.bgr2, inp.gabor2)
+        r.set_points(inp.pts1, inp.pts2)
+        r.render(phases, phases.astype(np.float64), plan.tri_idx, plan.tri_offsets)
+        frames = r.download(0, len(phases))
+        for k, s in enumerate(phases):
+            want, pts = ref.morph_images(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, float(s), float(s), levels)
+            assert bits_differ(frames[k], want) == 0, (chunk, k)
+            assert bits_differ(r.morphed_points(k), pts) == 0
+
+
+FRAME_FILES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
+                     if not os.path.basename(f).startswith(("chain_", "topology")))
+
+
+@pytest.mark.parametrize("path", FRAME_FILES, ids=[os.path.basename(f)[:-4] for f in FRAME_FILES])
+def test_golden_fixtures_on_gpu(path):
+    from poppy_b200 import renderer as R
+    g = np.load(path)
+    h, w = g["bgr1"].shape[:2]
+    s, m, levels = float(g["shape"]), float(g["mask_ratio"]), int(g["levels"])
+    tri = host.triangulate(host.morph_points(g["pts1"], g["pts2"], s, w, h), w, h)
+    assert (tri == g["tri_idx"]).all()
+    with R.MorphRenderer(w, h, levels, len(g["pts1"]), len(tri), 1, keep_stages=True) as r:
+        r.set_pair(g["bgr1"], g["bgr2"], g["gabor2"])
+        r.set_points(g["pts1"], g["pts2"])
+        cat, offs = flat_tri([tri])
+        r.render([s], [m], cat, offs)
+        assert bits_differ(r.download(0, 1)[0], g["dst"]) == 0
+        for stage, key in ((R.STAGE_MORPHED_POINTS, "morphed_points"), (R.STAGE_TRI_MAP, "tri_map"),
+                           (R.STAGE_WARPED1, "warped1"), (R.STAGE_WARPED2, "warped2"), (R.STAGE_MASK, "mask"),
+                           (R.STAGE_LAP_BLEND, "lap_blend")):
+            assert bits_differ(r.read_stage(stage, 0), g[key]) == 0, key
+
+
+def test_error_behaviour(native_lib):
+    from poppy_b200._lib import PoppyCudaError
+    from poppy_b200.renderer import MorphRenderer
+    w, h = 64, 48
+    inp = synth.make_inputs(w, h, 10, 3.0, seed=2)
+    tri = host.triangulate(host.morph_points(inp.pts1, inp.pts2, 0.5, w, h), w, h)
+    cat, offs = flat_tri([tri])
+    with MorphRenderer(w, h, 3, 32, 4, 2) as r:                      # room for 4 triangles only
+        with pytest.raises(PoppyCudaError) as e:
+            r.render([0.5], [0.5], cat, offs)                        # before set_pair / set_points
+        assert e.value.code == -4
+        r.set_pair(inp.bgr1, inp.bgr2, inp.gabor2)
+        r.set_points(inp.pts1, inp.pts2)
+        with pytest.raises(PoppyCudaError) as e:
+            r.render([0.5], [0.5], cat, offs)
+        assert e.value.code == -3                                    # capacity
+        with pytest.raises(PoppyCudaError) as e:
+            r.render([0.5] * 3, [0.5] * 3, np.zeros((0, 3), np.int32), [0, 0, 0, 0])
+        assert e.value.code == -3                                    # more frames than the ring holds
+    with MorphRenderer(w, h, 3, 32, 64, 1) as r:
+        r.set_pair(inp.bgr1, inp.bgr2, inp.gabor2)
+        r.set_points(inp.pts1, inp.pts2)
+        bad = cat.copy()
+        bad[0, 0] = 10_000
+        with pytest.raises(PoppyCudaError) as e:
+            r.render([0.5], [0.5], bad, offs)
+        assert e.value.code == -2                                    # vertex index out of range
+        with pytest.raises(PoppyCudaError):
+            r.set_points(np.zeros((100, 2), np.float32), np.zeros((100, 2), np.float32))   # > max_points
+    with pytest.raises(PoppyCudaError):
+        MorphRenderer(40000, 10, 3, 32, 64, 1)                       # cv::remap size limit

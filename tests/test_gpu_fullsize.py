@@ -1,0 +1,76 @@
+"""Full-size (BASELINE.json config 4: 3840x2160, 20k points, 6 levels) checks: two frames against the reference
+library, and size-independent properties — determinism, chunk-size independence through a device-side checksum,
+and the identity property (equal images + equal point sets => frames do not depend on the shape ratio)."""
+import numpy as np
+import pytest
+
+from poppy_b200 import host, synth
+from tests.util import assert_frame_parity, bits_differ
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def workload(native_lib):
+    c = synth.WORKLOADS["4k"]
+    inp = synth.make_inputs(c["w"], c["h"], c["n_points"], c["jitter"], c["seed"])
+    return c, inp
+
+
+def test_4k_frames_match_reference(workload):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("reference library not shipped")
+    from poppy_b200.renderer import MorphRenderer
+    c, inp = workload
+    w, h, L = c["w"], c["h"], c["levels"]
+    phases = np.array([0.25, 0.8], np.float32)
+    plan = host.SequencePlan(inp.pts1, inp.pts2, w, h, phases)
+    assert 39000 < plan.max_triangles < 41000
+    with MorphRenderer(w, h, L, len(inp.pts1), plan.max_triangles, 2) as r:
+        r.set_pair(inp.bgr1, inp.bgr2, inp.gabor2)
+        r.set_points(inp.pts1, inp.pts2)
+        r.render(phases, phases.astype(np.float64), plan.tri_idx, plan.tri_offsets)
+        frames = r.download(0, 2)
+    for k, s in enumerate(phases):
+        want, _ = ref.morph_images(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, float(s), float(s), L)
+        rep = assert_frame_parity(frames[k], want, f"4K phase {s}")
+        assert rep["differing_bytes"] == 0, rep
+
+
+def test_4k_determinism_and_chunk_independence(workload):
+    from poppy_b200.renderer import MorphRenderer
+    c, inp = workload
+    w, h, L = c["w"], c["h"], c["levels"]
+    phases = np.linspace(0.05, 0.95, 6).astype(np.float32)
+    plan = host.SequencePlan(inp.pts1, inp.pts2, w, h, phases)
+    sums = []
+    for chunk in (1, 6, 4):
+        with MorphRenderer(w, h, L, len(inp.pts1), plan.max_triangles, len(phases), chunk_frames=chunk) as r:
+            r.set_pair(inp.bgr1, inp.bgr2, inp.gabor2)
+            r.set_points(inp.pts1, inp.pts2)
+            r.render(phases, phases.astype(np.float64), plan.tri_idx, plan.tri_offsets)
+            a = r.checksum(0, len(phases))
+            r.render(phases, phases.astype(np.float64), plan.tri_idx, plan.tri_offsets)
+            assert r.checksum(0, len(phases)) == a, "render is not deterministic"
+            sums.append(a)
+            per_frame = [r.checksum(k, 1) for k in range(len(phases))]
+            assert len(set(per_frame)) == len(phases), "distinct phases must give distinct frames"
+    assert sums[0] == sums[1] == sums[2], "frames depend on the chunk size"
+
+
+def test_identity_property_full_size(workload):
+    """bgr1 == bgr2 and pts1 == pts2: every triangle maps onto itself, so both warps return the source and the
+    frame cannot depend on the shape ratio (mask ratio held fixed)."""
+    from poppy_b200.renderer import MorphRenderer
+    c, inp = workload
+    w, h, L = c["w"], c["h"], c["levels"]
+    shapes = np.array([0.0, 0.3, 0.9], np.float32)
+    masks = np.array([0.4, 0.4, 0.4], np.float64)
+    plan = host.SequencePlan(inp.pts1, inp.pts1, w, h, shapes)
+    with MorphRenderer(w, h, L, len(inp.pts1), plan.max_triangles, 3) as r:
+        r.set_pair(inp.bgr1, inp.bgr1, inp.gabor2)
+        r.set_points(inp.pts1, inp.pts1)
+        r.render(shapes, masks, plan.tri_idx, plan.tri_offsets)
+        s = [r.checksum(k, 1) for k in range(3)]
+    assert s[0] == s[1] == s[2]
