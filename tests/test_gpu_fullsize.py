@@ -1,6 +1,6 @@
 """Full-size (BASELINE.json config 4: 3840x2160, 20k points, 6 levels) checks: two frames against the reference
 library, and size-independent properties — determinism, chunk-size independence through a device-side checksum,
-and the identity property (equal images + equal point sets => frames do not depend on the shape ratio)."""
+and the mask-zero property (maskRatio = 0 => the frame ignores the pixels of image 2)."""
 import numpy as np
 import pytest
 
@@ -59,18 +59,22 @@ def test_4k_determinism_and_chunk_independence(workload):
     assert sums[0] == sums[1] == sums[2], "frames depend on the chunk size"
 
 
-def test_identity_property_full_size(workload):
-    """bgr1 == bgr2 and pts1 == pts2: every triangle maps onto itself, so both warps return the source and the
-    frame cannot depend on the shape ratio (mask ratio held fixed)."""
+def test_mask_zero_ignores_image2_full_size(workload):
+    """maskRatio = 0 makes lbmask exactly 1 at every pyramid level (pyrDown of a constant 1 is exactly 1), so the
+    right-hand pyramid is multiplied by exactly 0 everywhere: the frame must not depend on the pixels of image 2
+    (it still depends on the second point set through the mesh)."""
     from poppy_b200.renderer import MorphRenderer
     c, inp = workload
     w, h, L = c["w"], c["h"], c["levels"]
-    shapes = np.array([0.0, 0.3, 0.9], np.float32)
-    masks = np.array([0.4, 0.4, 0.4], np.float64)
-    plan = host.SequencePlan(inp.pts1, inp.pts1, w, h, shapes)
-    with MorphRenderer(w, h, L, len(inp.pts1), plan.max_triangles, 3) as r:
-        r.set_pair(inp.bgr1, inp.bgr1, inp.gabor2)
-        r.set_points(inp.pts1, inp.pts1)
-        r.render(shapes, masks, plan.tri_idx, plan.tri_offsets)
-        s = [r.checksum(k, 1) for k in range(3)]
-    assert s[0] == s[1] == s[2]
+    shapes = np.array([0.35, 0.8], np.float32)
+    masks = np.zeros(2, np.float64)
+    plan = host.SequencePlan(inp.pts1, inp.pts2, w, h, shapes)
+    sums = []
+    with MorphRenderer(w, h, L, len(inp.pts1), plan.max_triangles, 2) as r:
+        r.set_points(inp.pts1, inp.pts2)
+        for img2 in (inp.bgr2, np.ascontiguousarray(inp.bgr1[::-1])):
+            r.set_pair(inp.bgr1, img2, inp.gabor2)
+            r.render(shapes, masks, plan.tri_idx, plan.tri_offsets)
+            sums.append([r.checksum(k, 1) for k in range(2)])
+    assert sums[0] == sums[1]
+    assert sums[0][0] != sums[0][1]
