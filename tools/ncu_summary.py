@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Summarise ncu output into small text files that can be committed under profiles/.
+
+  python tools/ncu_summary.py launches gpurun_out/launches_TAG.csv   > profiles/rN_launches_TAG.txt
+  python tools/ncu_summary.py full     gpurun_out/prof_TAG.ncu-rep   > profiles/rN_ncu_full_TAG.txt
+"""
+import csv
+import io
+import re
+import subprocess
+import sys
+from collections import OrderedDict
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
+    "launch__grid_size", "launch__block_size", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "smsp__inst_executed.sum", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+]
+
+
+def short(name: str) -> str:
+    name = re.sub(r"^void\s+", "", name)
+    name = re.sub(r"\(.*$", "", name)
+    return name.replace("poppy::", "")
+
+
+def launches(path):
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr = rows[0]
+    ki, mi, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = OrderedDict()
+    for r in rows[1:]:
+        if r[mi] != "gpu__time_duration.sum":
+            continue
+        v = float(r[vi].replace(",", ""))
+        v = v / 1000.0 if r[ui] == "ns" else v
+        a = agg.setdefault(short(r[ki]), [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print(f"# ncu --metrics gpu__time_duration.sum --clock-control none  ({path}); cold-cache, serialised: compare SHARES")
+    print(f"{'kernel':40s} {'launches':>8s} {'total_us':>12s} {'us/launch':>10s} {'share':>7s}")
+    for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k:40s} {n:8d} {us:12.1f} {us / n:10.1f} {us / tot:7.3f}")
+    print(f"{'TOTAL':40s} {sum(a[0] for a in agg.values()):8d} {tot:12.1f}")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    print(f"# ncu --set full --clock-control none ({path}); per launch")
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        u = dict(zip(hdr, units))
+        print(f"== {short(d['Kernel Name'])}  grid {d.get('Grid Size')} block {d.get('Block Size')}")
+        for k in KEYS:
+            if k in d and d[k] != "":
+                print(f"   {k:85s} {d[k]:>16s} {u.get(k, '')}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
