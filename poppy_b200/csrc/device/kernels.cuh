@@ -20,17 +20,17 @@ void launch_raster_triangles(cudaStream_t st, const TriRaster* rast, const Frame
 // ---- kernels_warp.cu ---------------------------------------------------------------------------------------------
 // BGR (3 bytes/px, tight rows) -> BGRX uchar4
 void launch_bgr_to_bgrx(cudaStream_t st, const uint8_t* bgr, uchar4* out, int w, int h);
-// mask basis m2 = 1 - gray(gabor2)  (reference src/algo.cpp:250-252)
-void launch_mask_basis(cudaStream_t st, const float* gabor_bgr, float* m2, int w, int h);
-// create_map + remap for both images + lbmask of the frame (reference src/algo.cpp:232-238, 255-258).
+// mask basis m2 = 1 - gray(gabor2)  (reference src/algo.cpp:250-252), rows `bpitch` floats apart
+void launch_mask_basis(cudaStream_t st, const float* gabor_bgr, float* m2, int bpitch, int w, int h);
+// create_map + remap for both images (reference src/algo.cpp:232-238); warped rows are `wpitch` pixels apart
 void launch_warp(cudaStream_t st, const int* tri_map, const TriInverse* inv, int max_tri, const uchar4* src1,
-                 const uchar4* src2, const float* mask_basis, const FrameParams* fp, uint2* warped, float* mask0,
-                 int w, int h, int frames);
+                 const uchar4* src2, uint2* warped, int wpitch, int w, int h, int frames);
 
 // ---- kernels_pyramid.cu ------------------------------------------------------------------------------------------
-// level 0 -> 1: sources are the warped 8-bit pair (converted on the fly, algo.cpp:247-248) and mask0
-void launch_pyr_down0(cudaStream_t st, const uint2* warped, const float* mask0, int w, int h, float* dst,
-                      LevelDesc dl, int frames);
+// level 0 -> 1: sources are the warped 8-bit pair (converted on the fly, algo.cpp:247-248) and the frame's blend
+// mask evaluated from the mask basis (algo.cpp:255-258)
+void launch_pyr_down0(cudaStream_t st, const uint2* warped, int wpitch, const float* basis, int bpitch,
+                      const FrameParams* fp, int w, int h, float* dst, LevelDesc dl, int frames);
 // level k -> k+1 for the 7 planes (left BGR, right BGR, mask)
 void launch_pyr_down(cudaStream_t st, const float* src, LevelDesc sl, float* dst, LevelDesc dl, int frames);
 // resultSmallest = left*mask + right*(1-mask) at the coarsest level (blend.hpp:68-69)
@@ -38,9 +38,13 @@ void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* 
 // out[k] = pyrUp(out[k+1]) + (G_l[k]-pyrUp(G_l[k+1]))*m[k] + (G_r[k]-pyrUp(G_r[k+1]))*(1-m[k])   (blend.hpp:45-77)
 void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
                      LevelDesc cl, float* out_fine, int frames);
-// same for level 0, whose Gaussian level is the warped 8-bit pair + mask0
-void launch_collapse0(cudaStream_t st, const uint2* warped, const float* mask0, int w, int h, const float* g_coarse,
-                      const float* out_coarse, LevelDesc cl, float* out_fine, LevelDesc ol, int frames);
+// same for level 0, whose Gaussian level is the warped 8-bit pair + blend mask
+void launch_collapse0(cudaStream_t st, const uint2* warped, int wpitch, const float* basis, int bpitch,
+                      const FrameParams* fp, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
+                      float* out_fine, LevelDesc ol, int frames);
+// lbmask of frame `frame` as a tight w x h plane (stage dumps only)
+void launch_mask_plane(cudaStream_t st, const float* basis, int bpitch, const FrameParams* fp, int frame, float* out, int w,
+                       int h);
 
 // ---- kernels_unsharp.cu ------------------------------------------------------------------------------------------
 // unsharp_mask(lapBlend, 1, amount, 0.3) + convertTo(CV_8U, 255)   (reference src/algo.cpp:263-265, util.cpp:113-148)

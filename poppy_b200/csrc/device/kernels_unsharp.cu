@@ -12,20 +12,34 @@
 //   where ||diff||_2 >= 0.3 (cv::norm of a Vec3f: double accumulation + sqrt): x + amount*diff, else x
 //   (src/util.cpp:135-145, unfused); then cvRound(v*255) saturated to 8 bits (convert_scale.simd.hpp, saturate.hpp:105).
 //
-// One CTA produces a 32x16 output tile: the row pass is written to shared memory for the tile plus a
-// 1-pixel (median) + 4-row (Gaussian) halo, the column pass and the difference stay in shared memory, and the
-// packed BGR bytes are staged so that global stores are 32-bit and coalesced.
+// Design: one CTA walks a 120-column strip of the frame downwards, 8 rows per step, keeping three small rings in
+// shared memory (the input rows, their row-pass results, and the blur differences), so the 9x9 + 3x3 footprint costs
+// no vertical halo and every input value is read from global memory once (plus 8/120 horizontally). Per step:
+//   R  one warp per (row, channel): load 4 px per lane, exchange the horizontal neighbours through the input ring,
+//      row pass -> row-pass ring
+//   C  column pass with a 12-row register window per thread (4 columns x 4 rows), diff -> diff ring; a per-row bit
+//      mask records which 4-px groups hold any |diff| >= 0.17
+//   M  8 rows x 30 groups: where no flagged group touches the 3x3 window the median cannot reach the 0.3 threshold
+//      (|median| <= max |diff| < 0.3/sqrt(3)), so the pixel is the input; otherwise the exact median/norm/sharpen runs.
+//      Rounding to 8 bits uses the magic-number trick of pixel_ops.cuh; rows are written as three 32-bit words per lane.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "pixel_ops.cuh"
 
 namespace poppy {
 
 namespace {
 
-constexpr int TW = 32, TH = 16;
-constexpr int CW = TW + 2;            // cells per row: tile + median halo
-constexpr int TR = TH + 10;           // row-pass rows: tile + median halo + Gaussian halo
-constexpr int DR = TH + 2;
+constexpr int US_W = 120;            // output columns per strip
+constexpr int US_CW = 128;           // computed columns x0-4 .. x0+123
+constexpr int US_XW = 136;           // staged input columns x0-8 .. x0+127
+constexpr int US_STEP = 8;           // rows per step
+constexpr int US_RING = 16;          // ring depth of the input and row-pass rings
+constexpr int US_DRING = 12;         // ring depth of the diff ring
+constexpr int US_CHUNK = 216;        // rows per CTA
+constexpr size_t US_SMEM = ((size_t)US_RING * 3 * US_XW + (size_t)US_RING * 3 * US_CW + (size_t)US_DRING * 3 * US_CW) * sizeof(float) +
+                           US_DRING * sizeof(uint32_t);
+constexpr float US_FLAG_T = 0.17f;   // 3 * 0.17^2 = 0.0867 < 0.09: below this no median can reach the threshold
 
 // getGaussianKernel(9, 1, CV_32F) (bit-exact kernel, OCV imgproc/src/smooth.dispatch.cpp:81-198): centre .. edge
 __device__ __forceinline__ float gk(int j) {
@@ -45,129 +59,220 @@ __device__ __forceinline__ float median9(float p0, float p1, float p2, float p3,
 }
 #undef POPPY_SORT2
 
+// row filter at one pixel, fused (vector body) or unfused (scalar tail) — taps t[0..8] left to right
+__device__ __forceinline__ float row9(const float* t, bool fused) {
+    float s = __fmul_rn(gk(-4), t[0]);
+    if (fused) {
+#pragma unroll
+        for (int j = 1; j < 9; ++j) s = fmaf(t[j], gk(j - 4), s);
+    } else {
+#pragma unroll
+        for (int j = 1; j < 9; ++j) s = __fadd_rn(s, __fmul_rn(gk(j - 4), t[j]));
+    }
+    return s;
+}
+
+// symmetric column filter — w[0..8] top to bottom
+__device__ __forceinline__ float col9(float w0, float w1, float w2, float w3, float w4, float w5, float w6, float w7,
+                                      float w8, bool fused) {
+    if (fused) {
+        float s = fmaf(gk(0), w4, 0.f);
+        s = fmaf(gk(1), __fadd_rn(w5, w3), s);
+        s = fmaf(gk(2), __fadd_rn(w6, w2), s);
+        s = fmaf(gk(3), __fadd_rn(w7, w1), s);
+        return fmaf(gk(4), __fadd_rn(w8, w0), s);
+    }
+    float s = __fadd_rn(__fmul_rn(gk(0), w4), 0.f);
+    s = __fadd_rn(s, __fmul_rn(gk(1), __fadd_rn(w5, w3)));
+    s = __fadd_rn(s, __fmul_rn(gk(2), __fadd_rn(w6, w2)));
+    s = __fadd_rn(s, __fmul_rn(gk(3), __fadd_rn(w7, w1)));
+    return __fadd_rn(s, __fmul_rn(gk(4), __fadd_rn(w8, w0)));
+}
+
 }  // namespace
 
-// block 256; grid (ceil(w/32), ceil(h/16), frames). norm_thr2: smallest double whose sqrt is >= (double)0.3f.
-__global__ void __launch_bounds__(256)
-k_unsharp_store(const float* __restrict__ lap, int w, int h, int pitch, size_t stride,
-                const FrameParams* __restrict__ fp, double norm_thr2, uint8_t* __restrict__ frames_base,
-                size_t frame_bytes) {
-    __shared__ float s_row[TR][3][CW];
-    __shared__ float s_diff[DR][3][CW];
-    __shared__ __align__(4) uint8_t s_out[TH][TW * 3];
+// block 256; grid (ceil(w/120), ceil(h/216), frames); dynamic shared memory US_SMEM.
+// norm_thr2: smallest double whose sqrt is >= (double)0.3f.
+__global__ void __launch_bounds__(256, 3)
+k_unsharp_strip(const float* __restrict__ lap, int w, int h, int pitch, size_t stride, const FrameParams* __restrict__ fp,
+                double norm_thr2, uint8_t* __restrict__ frames_base, size_t frame_bytes) {
+    extern __shared__ __align__(16) float smem_dyn[];
+    float* xs = smem_dyn;                                        // [US_RING][3][US_XW]   input rows (virtual, reflected)
+    float* rp = xs + US_RING * 3 * US_XW;                        // [US_RING][3][US_CW]   row-pass results
+    float* df = rp + US_RING * 3 * US_CW;                        // [US_DRING][3][US_CW]  x - blur
+    uint32_t* fl = reinterpret_cast<uint32_t*>(df + US_DRING * 3 * US_CW);   // [US_DRING] flagged 4-px groups per diff row
 
-    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH, f = blockIdx.z;
-    const int tid = threadIdx.x;
-    const float* img = lap + (size_t)f * 3 * stride;
-    const int tail_from = 3 * w - (3 * w) % 8;      // first interleaved element handled by the scalar filter loops
-
-    // 1) row pass for every cell of the halo'd tile
-    for (int i = tid; i < TR * CW; i += 256) {
-        const int rj = i / CW, ci = i - rj * CW;
-        const int ry = ty0 - 5 + rj;
-        if (ry < 0 || ry >= h) continue;
-        const int gx = min(max(tx0 - 1 + ci, 0), w - 1);
-        int cx[9];
-#pragma unroll
-        for (int j = 0; j < 9; ++j) cx[j] = reflect101(gx - 4 + j, w);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float* row = img + (size_t)c * stride + (size_t)ry * pitch;
-            float s = __fmul_rn(gk(-4), __ldg(row + cx[0]));
-            if (w == 1) {
-                s = __ldg(row);          // GaussianBlur shrinks the kernel to [1] along a 1-pixel axis
-            } else if (3 * gx + c < tail_from) {
-#pragma unroll
-                for (int j = 1; j < 9; ++j) s = fmaf(__ldg(row + cx[j]), gk(j - 4), s);
-            } else {
-#pragma unroll
-                for (int j = 1; j < 9; ++j) s = __fadd_rn(s, __fmul_rn(gk(j - 4), __ldg(row + cx[j])));
-            }
-            s_row[rj][c][ci] = s;
-        }
-    }
-    __syncthreads();
-
-    // 2) column pass + difference at the (clamped) cell position
-    for (int i = tid; i < DR * CW; i += 256) {
-        const int dj = i / CW, ci = i - dj * CW;
-        const int gy = min(max(ty0 - 1 + dj, 0), h - 1);
-        const int gx = min(max(tx0 - 1 + ci, 0), w - 1);
-        const int base = ty0 - 5;
-        int rp[5], rm[5];
-#pragma unroll
-        for (int j = 1; j <= 4; ++j) { rp[j] = reflect101(gy + j, h) - base; rm[j] = reflect101(gy - j, h) - base; }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float s;
-            if (h == 1) {
-                s = s_row[gy - base][c][ci];
-            } else if (3 * gx + c < tail_from) {
-                s = fmaf(gk(0), s_row[gy - base][c][ci], 0.f);
-#pragma unroll
-                for (int j = 1; j <= 4; ++j) s = fmaf(gk(j), __fadd_rn(s_row[rp[j]][c][ci], s_row[rm[j]][c][ci]), s);
-            } else {
-                s = __fadd_rn(__fmul_rn(gk(0), s_row[gy - base][c][ci]), 0.f);
-#pragma unroll
-                for (int j = 1; j <= 4; ++j)
-                    s = __fadd_rn(s, __fmul_rn(gk(j), __fadd_rn(s_row[rp[j]][c][ci], s_row[rm[j]][c][ci])));
-            }
-            const float x = __ldg(img + (size_t)c * stride + (size_t)gy * pitch + gx);
-            s_diff[dj][c][ci] = __fsub_rn(x, s);
-        }
-    }
-    __syncthreads();
-
-    // 3) median, threshold, sharpen, 8-bit pack
+    const int f = blockIdx.z;
+    const int x0 = blockIdx.x * US_W, Y0 = blockIdx.y * US_CHUNK, Y1 = min(Y0 + US_CHUNK, h);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* __restrict__ img = lap + (size_t)f * 3 * stride;
+    const int tail_from = 3 * w - (3 * w) % 8;       // first interleaved element handled by the scalar filter loops
     const FrameParams P = fp[f];
-    for (int i = tid; i < TH * TW; i += 256) {
-        const int oy = i / TW, ox = i - oy * TW;
-        const int gx = tx0 + ox, gy = ty0 + oy;
-        if (gx >= w || gy >= h) continue;
-        float med[3];
-        double nn = 0.0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float* d0 = &s_diff[oy][c][ox];
-            const float* d1 = &s_diff[oy + 1][c][ox];
-            const float* d2 = &s_diff[oy + 2][c][ox];
-            med[c] = median9(d0[0], d0[1], d0[2], d1[0], d1[1], d1[2], d2[0], d2[1], d2[2]);
-            nn = __dadd_rn(nn, __dmul_rn((double)med[c], (double)med[c]));
-        }
-        const bool sharpen = nn >= norm_thr2;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float v = __ldg(img + (size_t)c * stride + (size_t)gy * pitch + gx);
-            if (sharpen) v = __fadd_rn(v, __fmul_rn(P.amount, med[c]));
-            const int q = cv_round(__fmul_rn(v, 255.f));
-            s_out[oy][ox * 3 + c] = (uint8_t)min(max(q, 0), 255);
-        }
-    }
-    __syncthreads();
-
-    // 4) coalesced store of the packed BGR rows
-    uint8_t* dst = frames_base + (size_t)P.dst_slot * frame_bytes;
-    const int cols = min(TW, w - tx0), rows = min(TH, h - ty0), row_bytes = cols * 3;
+    uint8_t* __restrict__ dst = frames_base + (size_t)P.dst_slot * frame_bytes;
     const size_t dst_pitch = (size_t)w * 3;
-    if ((dst_pitch & 3) == 0 && ((size_t)dst & 3) == 0) {
-        const int words = row_bytes >> 2;
-        for (int i = tid; i < rows * (TW * 3 / 4); i += 256) {
-            const int r = i / (TW * 3 / 4), wd = i - r * (TW * 3 / 4);
-            if (wd < words)
-                *reinterpret_cast<uint32_t*>(dst + (size_t)(ty0 + r) * dst_pitch + (size_t)tx0 * 3 + wd * 4) =
-                    *reinterpret_cast<const uint32_t*>(&s_out[r][wd * 4]);
-        }
-        const int tail = row_bytes & 3;
-        if (tail)
-            for (int i = tid; i < rows * tail; i += 256) {
-                const int r = i / tail, b = (row_bytes & ~3) + (i - r * tail);
-                dst[(size_t)(ty0 + r) * dst_pitch + (size_t)tx0 * 3 + b] = s_out[r][b];
+    const bool dst_words = (w & 3) == 0 && ((size_t)dst & 3) == 0;
+
+    // ring slots: virtual row v >= Y0 - 16 always
+    auto slot16 = [&](int v) { return (v - Y0 + 32) & (US_RING - 1); };
+    auto slot12 = [&](int v) { return (v - Y0 + 24) % US_DRING; };
+
+    const int gx0 = x0 - 4 + 4 * lane;               // this lane's 4 computed columns
+    // all 12 taps of the lane's 4 pixels inside the image, none of them in the scalar-tail region
+    const bool lane_fast = gx0 - 4 >= 0 && gx0 + 7 <= w - 1 && 3 * (gx0 + 3) + 2 < tail_from && w > 1;
+    const int n_steps = div_up(Y1 - Y0, US_STEP);
+
+    for (int s = -2; s < n_steps; ++s) {
+        const int vb = Y0 + US_STEP * s;             // step base row
+        // ---------------- R: row pass of virtual rows vb+5 .. vb+12 (those >= Y0-5) --------------------------------
+        for (int task = warp; task < US_STEP * 3; task += 8) {
+            const int v = vb + 5 + task / 3, c = task % 3;
+            if (v < Y0 - 5 || v > Y1 + 4) continue;
+            const float* __restrict__ row = img + (size_t)c * stride + (size_t)reflect101(v, h) * pitch;
+            float* xrow = xs + ((size_t)slot16(v) * 3 + c) * US_XW;
+            float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gx0 >= 0 && gx0 < w) {
+                own = __ldg(reinterpret_cast<const float4*>(row + gx0));
+                *reinterpret_cast<float4*>(xrow + 4 + 4 * lane) = own;
             }
-    } else {
-        for (int i = tid; i < rows * row_bytes; i += 256) {
-            const int r = i / row_bytes, b = i - r * row_bytes;
-            dst[(size_t)(ty0 + r) * dst_pitch + (size_t)tx0 * 3 + b] = s_out[r][b];
+            if (lane == 0 && x0 - 8 >= 0) *reinterpret_cast<float4*>(xrow) = __ldg(reinterpret_cast<const float4*>(row + x0 - 8));
+            if (lane == 1 && x0 + 124 < w)
+                *reinterpret_cast<float4*>(xrow + US_XW - 4) = __ldg(reinterpret_cast<const float4*>(row + x0 + 124));
+            __syncwarp();
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane_fast) {
+                const float4 lft = *reinterpret_cast<const float4*>(xrow + 4 * lane);
+                const float4 rgt = *reinterpret_cast<const float4*>(xrow + 8 + 4 * lane);
+                const float t[12] = {lft.x, lft.y, lft.z, lft.w, own.x, own.y, own.z, own.w, rgt.x, rgt.y, rgt.z, rgt.w};
+                o.x = row9(t + 0, true); o.y = row9(t + 1, true); o.z = row9(t + 2, true); o.w = row9(t + 3, true);
+            } else {
+                float r[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i) {
+                    const int gx = gx0 + i;
+                    if (gx < 0 || gx >= w) continue;
+                    if (w == 1) { r[i] = __ldg(row); continue; }      // GaussianBlur shrinks the kernel to [1] on a 1-pixel axis
+                    float t[9];
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) t[j] = __ldg(row + reflect101(gx - 4 + j, w));
+                    r[i] = row9(t, 3 * gx + c < tail_from);
+                }
+                o = make_float4(r[0], r[1], r[2], r[3]);
+            }
+            *reinterpret_cast<float4*>(rp + ((size_t)slot16(v) * 3 + c) * US_CW + 4 * lane) = o;
         }
+        if (tid < US_STEP) fl[slot12(vb + 1 + tid)] = 0u;
+        __syncthreads();
+
+        // ---------------- C: column pass + diff of rows vb+1 .. vb+8 -----------------------------------------------
+        if (warp < 6) {
+            const int c = warp >> 1, v0 = vb + 1 + 4 * (warp & 1);
+            const int lo = max(Y0 - 1, 0), hi = min(Y1, h - 1);          // diff rows needed by this CTA: [lo, hi]
+            if (v0 + 3 >= lo && v0 <= hi) {
+                float4 win[12];
+#pragma unroll
+                for (int j = 0; j < 12; ++j)
+                    win[j] = *reinterpret_cast<const float4*>(rp + ((size_t)slot16(v0 - 4 + j) * 3 + c) * US_CW + 4 * lane);
+                const bool fused = 3 * (gx0 + 3) + c < tail_from;         // whole group in the vector body
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int v = v0 + i;
+                    const bool need = v >= lo && v <= hi;                  // warp-uniform
+                    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                    bool big = false;
+                    if (need && gx0 >= 0 && gx0 < w) {
+                        float4 b;
+                        if (h == 1) {
+                            b = win[4 + i];
+                        } else if (fused) {
+                            b.x = col9(win[i].x, win[i + 1].x, win[i + 2].x, win[i + 3].x, win[i + 4].x, win[i + 5].x, win[i + 6].x, win[i + 7].x, win[i + 8].x, true);
+                            b.y = col9(win[i].y, win[i + 1].y, win[i + 2].y, win[i + 3].y, win[i + 4].y, win[i + 5].y, win[i + 6].y, win[i + 7].y, win[i + 8].y, true);
+                            b.z = col9(win[i].z, win[i + 1].z, win[i + 2].z, win[i + 3].z, win[i + 4].z, win[i + 5].z, win[i + 6].z, win[i + 7].z, win[i + 8].z, true);
+                            b.w = col9(win[i].w, win[i + 1].w, win[i + 2].w, win[i + 3].w, win[i + 4].w, win[i + 5].w, win[i + 6].w, win[i + 7].w, win[i + 8].w, true);
+                        } else {
+                            b.x = col9(win[i].x, win[i + 1].x, win[i + 2].x, win[i + 3].x, win[i + 4].x, win[i + 5].x, win[i + 6].x, win[i + 7].x, win[i + 8].x, 3 * (gx0 + 0) + c < tail_from);
+                            b.y = col9(win[i].y, win[i + 1].y, win[i + 2].y, win[i + 3].y, win[i + 4].y, win[i + 5].y, win[i + 6].y, win[i + 7].y, win[i + 8].y, 3 * (gx0 + 1) + c < tail_from);
+                            b.z = col9(win[i].z, win[i + 1].z, win[i + 2].z, win[i + 3].z, win[i + 4].z, win[i + 5].z, win[i + 6].z, win[i + 7].z, win[i + 8].z, 3 * (gx0 + 2) + c < tail_from);
+                            b.w = col9(win[i].w, win[i + 1].w, win[i + 2].w, win[i + 3].w, win[i + 4].w, win[i + 5].w, win[i + 6].w, win[i + 7].w, win[i + 8].w, 3 * (gx0 + 3) + c < tail_from);
+                        }
+                        const float4 x = *reinterpret_cast<const float4*>(xs + ((size_t)slot16(v) * 3 + c) * US_XW + 4 + 4 * lane);
+                        d = make_float4(__fsub_rn(x.x, b.x), __fsub_rn(x.y, b.y), __fsub_rn(x.z, b.z), __fsub_rn(x.w, b.w));
+                        // columns past the image hold padding: keep them out of the flags
+                        const float m0 = fabsf(d.x), m1 = gx0 + 1 < w ? fabsf(d.y) : 0.f, m2 = gx0 + 2 < w ? fabsf(d.z) : 0.f,
+                                    m3 = gx0 + 3 < w ? fabsf(d.w) : 0.f;
+                        big = !(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) < US_FLAG_T);
+                    }
+                    if (need) {
+                        *reinterpret_cast<float4*>(df + ((size_t)slot12(v) * 3 + c) * US_CW + 4 * lane) = d;
+                        const uint32_t bits = __ballot_sync(0xffffffffu, big);
+                        if (lane == 0 && bits) atomicOr(&fl[slot12(v)], bits);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---------------- M: median / threshold / sharpen / 8-bit store of rows vb .. vb+7 --------------------------
+        const int y = vb + warp, gx = x0 + 4 * lane;
+        if (s >= 0 && y < Y1 && lane < US_W / 4 && gx < w) {
+            const int ym = max(y - 1, 0), yp = min(y + 1, h - 1);
+            const int sm = slot12(ym), sc = slot12(y), sp = slot12(yp);
+            // computed-column group of gx is lane+1; its 3x3 windows reach groups lane .. lane+2
+            const uint32_t flagged = (fl[sm] | fl[sc] | fl[sp]) & (7u << lane);
+            const float* xrow = xs + (size_t)slot16(y) * 3 * US_XW + 8 + 4 * lane;
+            float4 px[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) px[c] = *reinterpret_cast<const float4*>(xrow + c * US_XW);
+            float v[3][4] = {{px[0].x, px[0].y, px[0].z, px[0].w}, {px[1].x, px[1].y, px[1].z, px[1].w}, {px[2].x, px[2].y, px[2].z, px[2].w}};
+            const int npx = min(4, w - gx);
+            if (flagged) {
+#pragma unroll 1
+                for (int i = 0; i < npx; ++i) {
+                    const int cc = 4 + 4 * lane + i;                            // column in the diff ring
+                    const int cm = max(gx + i - 1, 0) - (x0 - 4), cp = min(gx + i + 1, w - 1) - (x0 - 4);
+                    float med[3];
+                    double nn = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float* d0 = df + ((size_t)sm * 3 + c) * US_CW;
+                        const float* d1 = df + ((size_t)sc * 3 + c) * US_CW;
+                        const float* d2 = df + ((size_t)sp * 3 + c) * US_CW;
+                        med[c] = median9(d0[cm], d0[cc], d0[cp], d1[cm], d1[cc], d1[cp], d2[cm], d2[cc], d2[cp]);
+                        nn = __dadd_rn(nn, __dmul_rn((double)med[c], (double)med[c]));
+                    }
+                    if (nn >= norm_thr2) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float add = __fmul_rn(P.amount, med[c]);
+                            // static indexing keeps v[][] in registers
+                            if (i == 0) v[c][0] = __fadd_rn(v[c][0], add);
+                            else if (i == 1) v[c][1] = __fadd_rn(v[c][1], add);
+                            else if (i == 2) v[c][2] = __fadd_rn(v[c][2], add);
+                            else v[c][3] = __fadd_rn(v[c][3], add);
+                        }
+                    }
+                }
+            }
+            float q[3][4];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[c][i] = u8_magic(v[c][i]);
+            uint8_t* drow = dst + (size_t)y * dst_pitch + (size_t)gx * 3;
+            if (dst_words && npx == 4) {
+                uint32_t* d32 = reinterpret_cast<uint32_t*>(drow);
+                d32[0] = pack_u8x4(q[0][0], q[1][0], q[2][0], q[0][1]);
+                d32[1] = pack_u8x4(q[1][1], q[2][1], q[0][2], q[1][2]);
+                d32[2] = pack_u8x4(q[2][2], q[0][3], q[1][3], q[2][3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < npx) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) drow[3 * i + c] = (uint8_t)(__float_as_uint(q[c][i]) & 255u);
+                    }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -197,7 +302,12 @@ void launch_unsharp_store(cudaStream_t st, const float* lap_blend, LevelDesc l, 
         while (__builtin_sqrt(s) < t) s = __builtin_nextafter(s, 1.0);
         return s;
     }();
-    k_unsharp_store<<<dim3(div_up(l.w, TW), div_up(l.h, TH), frames), 256, 0, st>>>(
+    static bool once = false;
+    if (!once) {
+        cudaFuncSetAttribute(k_unsharp_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)US_SMEM);
+        once = true;
+    }
+    k_unsharp_strip<<<dim3(div_up(l.w, US_W), div_up(l.h, US_CHUNK), frames), 256, US_SMEM, st>>>(
         lap_blend, l.w, l.h, l.pitch, l.plane_stride, fp, thr2, frames_base, frame_bytes);
 }
 

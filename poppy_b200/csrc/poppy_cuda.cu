@@ -1,12 +1,13 @@
 // poppy_cuda.cu — context, HBM layout and the extern "C" layer declared in include/poppy_cuda.h.
 //
 // HBM layout per context (W x H frame, L pyramid levels, chunk of B frames in flight):
-//   pair (resident)   : src1, src2 as BGRX uchar4 [H][W]; mask basis m2 float [H][W]; clipped point sets
+//   pair (resident)   : src1, src2 as BGRX uchar4 [H][W]; mask basis m2 float [H][pitch0]; clipped point sets
+//                       (pitch0 = W rounded up to 32 elements: rows of every per-pixel plane start 128-byte aligned)
 //   frame ring        : max_batch_frames x [H][W*3] 8-bit BGR — the rendered frames stay in HBM until downloaded
 //   morphed points    : max_batch_frames x max_points float2
 //   chunk scratch (xB): FrameParams; triangle indices; TriInverse / TriRaster records; triangle-ID map int32 [H][W];
-//                       warped pair uint2 [H][W]; mask plane float [H][W]; Gaussian levels 1..L (7 planes);
-//                       collapsed levels 0..L (3 planes)
+//                       warped pair uint2 [H][pitch0]; Gaussian levels 1..L (7 planes); collapsed levels 0..L
+//                       (3 planes); the level-0 mask plane exists only for stage dumps
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -75,6 +76,8 @@ struct poppy_cuda_ctx {
 
     size_t frame_bytes() const { return (size_t)w * h * 3; }
     size_t pixels() const { return (size_t)w * h; }
+    int pitch0() const { return lv[0].pitch; }
+    size_t padded_pixels() const { return lv[0].plane_stride; }
 };
 
 namespace {
@@ -108,7 +111,7 @@ void free_chunk(poppy_cuda_ctx* c) {
 }
 
 size_t per_frame_scratch_bytes(const poppy_cuda_ctx* c) {
-    return c->pixels() * (4 + 8 + 4) + (c->g_floats + c->o_floats) * 4 +
+    return c->pixels() * 4 + c->padded_pixels() * 8 + (c->g_floats + c->o_floats) * 4 +
            (size_t)c->max_tri * (sizeof(int3) + sizeof(TriInverse) + sizeof(TriRaster));
 }
 
@@ -129,8 +132,8 @@ int ensure_chunk(poppy_cuda_ctx* c) {
     CU_TRY(c, dmalloc(&c->d_inv, B * c->max_tri));
     CU_TRY(c, dmalloc(&c->d_rast, B * c->max_tri));
     CU_TRY(c, dmalloc(&c->d_trimap, B * c->pixels()));
-    CU_TRY(c, dmalloc(&c->d_warped, B * c->pixels()));
-    CU_TRY(c, dmalloc(&c->d_mask0, B * c->pixels()));
+    CU_TRY(c, dmalloc(&c->d_warped, B * c->padded_pixels()));
+    CU_TRY(c, dmalloc(&c->d_mask0, c->keep_stages ? c->pixels() : 1));
     CU_TRY(c, dmalloc(&c->d_g, B * c->g_floats));
     CU_TRY(c, dmalloc(&c->d_o, B * c->o_floats));
     for (int i = 0; i < 2; ++i) {
@@ -224,11 +227,10 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
         launch_raster_triangles(st, c->d_rast, c->d_fp, c->max_tri, tri_max, nb, c->d_trimap, w, h);
     }
     {   Scope s(c, KC_WARP);
-        launch_warp(st, c->d_trimap, c->d_inv, c->max_tri, src1, c->d_src2, c->d_mbasis, c->d_fp, c->d_warped,
-                    c->d_mask0, w, h, nb);
+        launch_warp(st, c->d_trimap, c->d_inv, c->max_tri, src1, c->d_src2, c->d_warped, c->pitch0(), w, h, nb);
     }
     {   Scope s(c, KC_PYR_DOWN);
-        launch_pyr_down0(st, c->d_warped, c->d_mask0, w, h, g_level(c, 1), c->lv[1], nb);
+        launch_pyr_down0(st, c->d_warped, c->pitch0(), c->d_mbasis, c->pitch0(), c->d_fp, w, h, g_level(c, 1), c->lv[1], nb);
     }
     for (int k = 1; k < L; ++k) {
         Scope s(c, KC_PYR_DOWN);
@@ -242,8 +244,8 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
         launch_collapse(st, g_level(c, k), c->lv[k], g_level(c, k + 1), o_level(c, k + 1), c->lv[k + 1], o_level(c, k), nb);
     }
     {   Scope s(c, KC_COLLAPSE);
-        launch_collapse0(st, c->d_warped, c->d_mask0, w, h, g_level(c, 1), o_level(c, 1), c->lv[1], o_level(c, 0),
-                         c->lv[0], nb);
+        launch_collapse0(st, c->d_warped, c->pitch0(), c->d_mbasis, c->pitch0(), c->d_fp, w, h, g_level(c, 1),
+                         o_level(c, 1), c->lv[1], o_level(c, 0), c->lv[0], nb);
     }
     {   Scope s(c, KC_UNSHARP);
         launch_unsharp_store(st, o_level(c, 0), c->lv[0], c->d_fp, c->d_frames, c->frame_bytes(), nb);
@@ -311,7 +313,7 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
     CR_TRY(dmalloc(&c->d_src1, px));
     CR_TRY(dmalloc(&c->d_src2, px));
     CR_TRY(dmalloc(&c->d_src_chain, px));
-    CR_TRY(dmalloc(&c->d_mbasis, px));
+    CR_TRY(dmalloc(&c->d_mbasis, c->padded_pixels()));
     CR_TRY(dmalloc(&c->d_pts1_raw, (size_t)max_points));
     CR_TRY(dmalloc(&c->d_pts2_raw, (size_t)max_points));
     CR_TRY(dmalloc(&c->d_pts1, (size_t)max_points));
@@ -391,7 +393,7 @@ int poppy_cuda_set_pair(poppy_cuda_ctx* c, const uint8_t* bgr1, size_t step1, co
         CU_TRY(c, cudaMemcpy2DAsync(stage, row, bgr2, step2, row, c->h, cudaMemcpyHostToDevice, c->stream));
         launch_bgr_to_bgrx(c->stream, stage, c->d_src2, c->w, c->h);
         CU_TRY(c, cudaMemcpy2DAsync(gstage, grow, gabor, gstep, grow, c->h, cudaMemcpyHostToDevice, c->stream));
-        launch_mask_basis(c->stream, gstage, c->d_mbasis, c->w, c->h);
+        launch_mask_basis(c->stream, gstage, c->d_mbasis, c->pitch0(), c->w, c->h);
         c->launches += 3; c->class_launches[KC_MISC] += 3;
         CU_TRY(c, cudaGetLastError());
         CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -571,7 +573,8 @@ int poppy_cuda_debug_read(poppy_cuda_ctx* c, int stage, int frame, void* dst, si
     case POPPY_STAGE_WARPED2: {
         if (int rc = need(px * 3)) return rc;
         std::vector<uint2> tmp(px);
-        CU_TRY(c, cudaMemcpy(tmp.data(), c->d_warped, px * 8, cudaMemcpyDeviceToHost));
+        CU_TRY(c, cudaMemcpy2D(tmp.data(), (size_t)w * 8, c->d_warped, (size_t)c->pitch0() * 8, (size_t)w * 8, h,
+                               cudaMemcpyDeviceToHost));
         uint8_t* o = (uint8_t*)dst;
         for (size_t i = 0; i < px; ++i) {
             uint32_t v = stage == POPPY_STAGE_WARPED1 ? tmp[i].x : tmp[i].y;
@@ -581,6 +584,9 @@ int poppy_cuda_debug_read(poppy_cuda_ctx* c, int stage, int frame, void* dst, si
     }
     case POPPY_STAGE_MASK:
         if (int rc = need(px * 4)) return rc;
+        launch_mask_plane(c->stream, c->d_mbasis, c->pitch0(), c->d_fp, 0, c->d_mask0, w, h);
+        CU_TRY(c, cudaGetLastError());
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
         CU_TRY(c, cudaMemcpy(dst, c->d_mask0, bytes, cudaMemcpyDeviceToHost));
         return 0;
     case POPPY_STAGE_LAP_BLEND: {

@@ -18,6 +18,11 @@ CASES = [
     (100, 75, 20, 1.0, 6),
     (333, 222, 50, 0.123, 3),
     (64, 48, 12, 0.5, 2),
+    # sizes that exercise the vectorised tile interiors (several tiles / strips / row chunks) and their edges
+    (1024, 600, 500, 0.3, 6),
+    (508, 436, 200, 0.6, 5),
+    (1280, 720, 800, 0.71, 64),
+    (250, 1100, 150, 0.45, 7),
 ]
 
 

@@ -5,7 +5,7 @@ TAG=${1:-run}
 KRE=${2:-}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25
 timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3
 timeout 900 python bench.py --frames 96 --steps 3 --warmup 3 --cpu-frames 2 --e2e-steps 1 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; tail -c 3500 gpurun_out/bench_${TAG}.json; tail -5 gpurun_out/bench_${TAG}.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv \
