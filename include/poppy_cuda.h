@@ -67,6 +67,10 @@ int poppy_cuda_get_info(const poppy_cuda_ctx* ctx, int* width, int* height, int*
 int poppy_cuda_set_keep_stages(poppy_cuda_ctx* ctx, int keep);       /* 1: chunk size 1, stage buffers readable */
 int poppy_cuda_set_chunk_frames(poppy_cuda_ctx* ctx, int frames);    /* frames rendered per kernel batch (>=1) */
 int poppy_cuda_set_stage_timing(poppy_cuda_ctx* ctx, int enable);    /* CUDA-event timing per kernel class */
+/* Capacity (entries per frame) of the per-tile triangle lists that feed the rasteriser. The default suits any
+ * Delaunay mesh; a frame whose lists do not fit is still rendered exactly (every tile then tests every triangle of
+ * that frame), only slower. Exposed so that this path can be exercised by the tests. */
+int poppy_cuda_set_tile_list_capacity(poppy_cuda_ctx* ctx, int entries_per_frame);
 
 /* corrected1 / corrected2 (8UC3 BGR, row stride in bytes) and gabor2 (32FC3 BGR in [0,1], row stride in bytes) of
  * one image pair: the Mat arguments of morph_images (reference src/algo.cpp:178). H2D once per pair. */

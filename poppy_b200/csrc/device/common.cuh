@@ -52,6 +52,9 @@ struct LevelDesc {
 
 __host__ __device__ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
+// Screen tile of the fused rasterise-and-warp kernel (one CTA per tile) and of the triangle binning that feeds it.
+constexpr int RW_TW = 64, RW_TH = 32;
+
 // cv::borderInterpolate(BORDER_REFLECT_101), OCV core/src/copy.cpp:748-793
 __device__ __forceinline__ int reflect101(int p, int len) {
     if ((unsigned)p < (unsigned)len) return p;

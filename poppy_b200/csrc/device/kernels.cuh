@@ -12,25 +12,32 @@ void launch_lerp_points(cudaStream_t st, const float2* p1, size_t p1_frame_strid
                         int rows);
 void launch_tri_geometry(cudaStream_t st, const int3* tri_idx, const FrameParams* fp, const float2* p1,
                          size_t p1_frame_stride, const float2* p2, const float2* morphed, size_t morphed_frame_stride,
-                         int max_tri, int tri_in_chunk_max, int frames, int img_h, TriInverse* inv_out,
-                         TriRaster* rast_out);
-void launch_raster_triangles(cudaStream_t st, const TriRaster* rast, const FrameParams* fp, int max_tri,
-                             int tri_in_chunk_max, int frames, int* tri_map, int w, int h);
+                         int max_tri, int tri_in_chunk_max, int frames, int img_w, int img_h, TriInverse* inv_out,
+                         TriRaster* rast_out, int* tile_counts);
+// tile_counts (frames x n_tiles, filled by launch_tri_geometry) -> tile_off (frames x (n_tiles+1)), overflow (frames),
+// tile_list (frames x cap)
+void launch_bin_triangles(cudaStream_t st, const TriRaster* rast, const FrameParams* fp, int max_tri, int tri_in_chunk_max,
+                          int frames, int img_w, int img_h, int* tile_counts, int* tile_off, int* overflow, int* tile_list,
+                          int cap);
 
 // ---- kernels_warp.cu ---------------------------------------------------------------------------------------------
 // BGR (3 bytes/px, tight rows) -> BGRX uchar4
 void launch_bgr_to_bgrx(cudaStream_t st, const uint8_t* bgr, uchar4* out, int w, int h);
 // mask basis m2 = 1 - gray(gabor2)  (reference src/algo.cpp:250-252), rows `bpitch` floats apart
 void launch_mask_basis(cudaStream_t st, const float* gabor_bgr, float* m2, int bpitch, int w, int h);
-// create_map + remap for both images (reference src/algo.cpp:232-238); warped rows are `wpitch` pixels apart
-void launch_warp(cudaStream_t st, const int* tri_map, const TriInverse* inv, int max_tri, const uchar4* src1,
-                 const uchar4* src2, uint2* warped, int wpitch, int w, int h, int frames);
+// paint_triangles + create_map + remap for both images, one CTA per 64x32 screen tile (reference src/algo.cpp:95-106,
+// 146-176, 232-238); warped rows are `wpitch` pixels apart; tri_map_out (nullable) receives frame 0's ID map
+void launch_raster_warp(cudaStream_t st, const TriRaster* rast, const TriInverse* inv, const FrameParams* fp, int max_tri,
+                        const int* tile_off, const int* tile_list, int cap, const int* overflow, const uchar4* src1,
+                        const uchar4* src2, uint2* warped, int wpitch, int* tri_map_out, int w, int h, int frames);
 
 // ---- kernels_pyramid.cu ------------------------------------------------------------------------------------------
 // level 0 -> 1: sources are the warped 8-bit pair (converted on the fly, algo.cpp:247-248) and the frame's blend
-// mask evaluated from the mask basis (algo.cpp:255-258)
+// mask evaluated from the mask basis (algo.cpp:255-258); the level-0 mask is also kept in mask0 (per-frame planes,
+// rows bpitch floats apart, m0stride floats per frame) for launch_collapse0
 void launch_pyr_down0(cudaStream_t st, const uint2* warped, int wpitch, const float* basis, int bpitch,
-                      const FrameParams* fp, int w, int h, float* dst, LevelDesc dl, int frames);
+                      const FrameParams* fp, int w, int h, float* mask0, size_t m0stride, float* dst, LevelDesc dl,
+                      int frames);
 // level k -> k+1 for the 7 planes (left BGR, right BGR, mask)
 void launch_pyr_down(cudaStream_t st, const float* src, LevelDesc sl, float* dst, LevelDesc dl, int frames);
 // resultSmallest = left*mask + right*(1-mask) at the coarsest level (blend.hpp:68-69)
@@ -38,13 +45,10 @@ void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* 
 // out[k] = pyrUp(out[k+1]) + (G_l[k]-pyrUp(G_l[k+1]))*m[k] + (G_r[k]-pyrUp(G_r[k+1]))*(1-m[k])   (blend.hpp:45-77)
 void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
                      LevelDesc cl, float* out_fine, int frames);
-// same for level 0, whose Gaussian level is the warped 8-bit pair + blend mask
-void launch_collapse0(cudaStream_t st, const uint2* warped, int wpitch, const float* basis, int bpitch,
-                      const FrameParams* fp, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
-                      float* out_fine, LevelDesc ol, int frames);
-// lbmask of frame `frame` as a tight w x h plane (stage dumps only)
-void launch_mask_plane(cudaStream_t st, const float* basis, int bpitch, const FrameParams* fp, int frame, float* out, int w,
-                       int h);
+// same for level 0, whose Gaussian level is the warped 8-bit pair + the level-0 mask planes
+void launch_collapse0(cudaStream_t st, const uint2* warped, int wpitch, const float* mask0, int mpitch, size_t m0stride,
+                      int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl, float* out_fine,
+                      LevelDesc ol, int frames);
 
 // ---- kernels_unsharp.cu ------------------------------------------------------------------------------------------
 // unsharp_mask(lapBlend, 1, amount, 0.3) + convertTo(CV_8U, 255)   (reference src/algo.cpp:263-265, util.cpp:113-148)

@@ -5,8 +5,8 @@
 //   k_tri_geometry     make_triangler_points, solve_homography, morph_homography, the Mat::inv of create_map
 //                                                           reference src/algo.cpp:83-93,108-144,154-157
 //                      + closed form of cv::FillConvexPoly's edge walkers (OCV drawing.cpp:1093-1255)
-//   k_raster_triangles paint_triangles(): Bresenham outline + 16.16 DDA span fill, "later triangle wins"
-//                      resolved with atomicMax             reference src/algo.cpp:95-106
+//   k_bin_scan/_fill   per-frame lists of the triangles touching each 64x32 screen tile (feeds k_raster_warp,
+//                      kernels_warp.cu, which paints the triangle-ID tile in shared memory)
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -138,11 +138,22 @@ __device__ void make_fill_record(TriRaster& r, int img_h) {
     r.yend = (short)yend;
 }
 
-// grid (ceil(max_tri/128), frames)
+// Screen tiles (RW_TW x RW_TH pixels) a triangle's bounding box touches; false when it lies outside the image.
+__device__ __forceinline__ bool tile_bbox(const TriRaster& r, int w, int h, int& tx0, int& tx1, int& ty0, int& ty1) {
+    const int x0 = max(min(min(r.vx[0], r.vx[1]), r.vx[2]), 0), x1 = min(max(max(r.vx[0], r.vx[1]), r.vx[2]), w - 1);
+    const int y0 = max(min(min(r.vy[0], r.vy[1]), r.vy[2]), 0), y1 = min(max(max(r.vy[0], r.vy[1]), r.vy[2]), h - 1);
+    if (x0 > x1 || y0 > y1) return false;
+    tx0 = x0 / RW_TW; tx1 = x1 / RW_TW; ty0 = y0 / RW_TH; ty1 = y1 / RW_TH;
+    return true;
+}
+
+// grid (ceil(max_tri/128), frames). tile_counts (frames x n_tiles, zeroed by the caller) receives, per screen tile,
+// the number of triangles whose bounding box touches it.
 __global__ void k_tri_geometry(const int3* __restrict__ tri_idx, const FrameParams* __restrict__ fp,
                                const float2* __restrict__ p1, size_t p1_frame_stride, const float2* __restrict__ p2,
-                               const float2* __restrict__ morphed, size_t morphed_frame_stride, int max_tri, int img_h,
-                               TriInverse* __restrict__ inv_out, TriRaster* __restrict__ rast_out) {
+                               const float2* __restrict__ morphed, size_t morphed_frame_stride, int max_tri, int img_w,
+                               int img_h, TriInverse* __restrict__ inv_out, TriRaster* __restrict__ rast_out,
+                               int* __restrict__ tile_counts, int tiles_x, int n_tiles) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int f = blockIdx.y;
     FrameParams P = fp[f];
@@ -163,6 +174,12 @@ __global__ void k_tri_geometry(const int3* __restrict__ tri_idx, const FramePara
     }
     make_fill_record(R, img_h);
     rast_out[(size_t)f * max_tri + t] = R;
+    {
+        int tx0, tx1, ty0, ty1;
+        if (tile_bbox(R, img_w, img_h, tx0, tx1, ty0, ty1))
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&tile_counts[(size_t)f * n_tiles + ty * tiles_x + tx], 1);
+    }
 
     float iP1[9], H[9], iH[9], M1[9], M2[9];
     inv3(P1, iP1);
@@ -183,52 +200,71 @@ __global__ void k_tri_geometry(const int3* __restrict__ tri_idx, const FramePara
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Exact fillConvexPoly(img32S, tri, i+1) for all triangles of a frame chunk, one warp per triangle.
-// 8-connected Bresenham outline (closed form of LineIterator, OCV imgproc.hpp:4956-4970 / drawing.cpp:159-260):
-// step i of an edge sits at major = start + i, minor = start + sign * ((2*minor_len*i + major_len - 1) / (2*major_len)).
-// grid.x covers warps over max_tri, grid.y = frames.
-__global__ void k_raster_triangles(const TriRaster* __restrict__ rast, const FrameParams* __restrict__ fp, int max_tri,
-                                   int* __restrict__ tri_map, int w, int h) {
-    const int lane = threadIdx.x & 31;
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int f = blockIdx.y;
-    if (t >= fp[f].n_tri) return;
-    const TriRaster R = rast[(size_t)f * max_tri + t];
-    int* map = tri_map + (size_t)f * w * h;
-    const int color = t + 1;
-
+// Tile binning. k_bin_scan: per frame, exclusive prefix sum of the tile counts -> tile_off (n_tiles + 1 entries);
+// a frame whose lists would not fit `cap` entries is flagged (the raster kernel then tests every triangle).
+// block 1024; grid frames.
+__global__ void __launch_bounds__(1024)
+k_bin_scan(const int* __restrict__ tile_counts, int n_tiles, int cap, int* __restrict__ tile_off, int* __restrict__ overflow) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* cnt = tile_counts + (size_t)f * n_tiles;
+    int* off = tile_off + (size_t)f * (n_tiles + 1);
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n_tiles ? cnt[i] : 0;
+        int incl = v;
 #pragma unroll
-    for (int e = 0; e < 3; ++e) {
-        int x0 = R.vx[(e + 2) % 3], y0 = R.vy[(e + 2) % 3], x1 = R.vx[e], y1 = R.vy[e];
-        int dx = x1 - x0, dy = y1 - y0, sy = 1;
-        if (dx < 0) { dx = -dx; dy = -dy; x0 = x1; y0 = y1; }
-        if (dy < 0) { dy = -dy; sy = -1; }
-        const bool steep = dy > dx;
-        const int major = steep ? dy : dx, minor = steep ? dx : dy;
-        for (int i = lane; i <= major; i += 32) {
-            int m = major > 0 ? (2 * minor * i + major - 1) / (2 * major) : 0;
-            int x = steep ? x0 + m : x0 + i;
-            int y = steep ? y0 + sy * i : y0 + sy * m;
-            if ((unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h) atomicMax(&map[(size_t)y * w + x], color);
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
         }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int ws = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += n;
+            }
+            warp_sums[lane] = ws;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + (warp ? warp_sums[warp - 1] : 0) + incl - v;
+        if (i < n_tiles) off[i] = excl;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + warp_sums[31];
+        __syncthreads();
     }
-    for (int y = R.ymin + lane; y < R.yend; y += 32) {
-        if (y < 0) continue;
-        long long xa, xb;
-        {
-            int j = y >= R.sw[0] ? 1 : 0, ys = j ? R.sw[0] : R.ymin;
-            xa = (long long)R.x0[0][j] + (long long)(y - ys) * R.dx[0][j];
-            j = y >= R.sw[1] ? 1 : 0; ys = j ? R.sw[1] : R.ymin;
-            xb = (long long)R.x0[1][j] + (long long)(y - ys) * R.dx[1][j];
-        }
-        long long xl = xa > xb ? xb : xa, xr = xa > xb ? xa : xb;
-        int xx1 = (int)((xl + 32768) >> 16), xx2 = (int)((xr + 32768) >> 16);
-        if (xx2 >= 0 && xx1 < w) {
-            xx1 = max(xx1, 0);
-            xx2 = min(xx2, w - 1);
-            for (int x = xx1; x <= xx2; ++x) atomicMax(&map[(size_t)y * w + x], color);
-        }
+    if (tid == 0) {
+        off[n_tiles] = carry_s;
+        overflow[f] = carry_s > cap ? 1 : 0;
     }
+}
+
+// grid (ceil(max_tri/128), frames): scatter triangle ids into their tiles' lists; tile_counts is consumed as the
+// fill cursor (counted down to zero).
+__global__ void k_bin_fill(const TriRaster* __restrict__ rast, const FrameParams* __restrict__ fp, int max_tri, int img_w,
+                           int img_h, int* __restrict__ tile_counts, const int* __restrict__ tile_off,
+                           const int* __restrict__ overflow, int* __restrict__ tile_list, int cap, int tiles_x, int n_tiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (t >= fp[f].n_tri || overflow[f]) return;
+    const TriRaster& R = rast[(size_t)f * max_tri + t];
+    TriRaster r;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r.vx[k] = R.vx[k]; r.vy[k] = R.vy[k]; }
+    int tx0, tx1, ty0, ty1;
+    if (!tile_bbox(r, img_w, img_h, tx0, tx1, ty0, ty1)) return;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) {
+            const int tile = ty * tiles_x + tx;
+            const int pos = atomicSub(&tile_counts[(size_t)f * n_tiles + tile], 1) - 1;
+            tile_list[(size_t)f * cap + tile_off[(size_t)f * (n_tiles + 1) + tile] + pos] = t;
+        }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -246,17 +282,24 @@ void launch_lerp_points(cudaStream_t st, const float2* p1, size_t p1_frame_strid
 
 void launch_tri_geometry(cudaStream_t st, const int3* tri_idx, const FrameParams* fp, const float2* p1,
                          size_t p1_frame_stride, const float2* p2, const float2* morphed, size_t morphed_frame_stride,
-                         int max_tri, int tri_in_chunk_max, int frames, int img_h, TriInverse* inv_out,
-                         TriRaster* rast_out) {
+                         int max_tri, int tri_in_chunk_max, int frames, int img_w, int img_h, TriInverse* inv_out,
+                         TriRaster* rast_out, int* tile_counts) {
+    const int tiles_x = div_up(img_w, RW_TW), n_tiles = tiles_x * div_up(img_h, RW_TH);
     if (tri_in_chunk_max > 0)
         k_tri_geometry<<<dim3(div_up(tri_in_chunk_max, 128), frames), 128, 0, st>>>(
-            tri_idx, fp, p1, p1_frame_stride, p2, morphed, morphed_frame_stride, max_tri, img_h, inv_out, rast_out);
+            tri_idx, fp, p1, p1_frame_stride, p2, morphed, morphed_frame_stride, max_tri, img_w, img_h, inv_out, rast_out,
+            tile_counts, tiles_x, n_tiles);
 }
 
-void launch_raster_triangles(cudaStream_t st, const TriRaster* rast, const FrameParams* fp, int max_tri,
-                             int tri_in_chunk_max, int frames, int* tri_map, int w, int h) {
+void launch_bin_triangles(cudaStream_t st, const TriRaster* rast, const FrameParams* fp, int max_tri, int tri_in_chunk_max,
+                          int frames, int img_w, int img_h, int* tile_counts, int* tile_off, int* overflow, int* tile_list,
+                          int cap) {
+    const int tiles_x = div_up(img_w, RW_TW), n_tiles = tiles_x * div_up(img_h, RW_TH);
+    k_bin_scan<<<frames, 1024, 0, st>>>(tile_counts, n_tiles, cap, tile_off, overflow);
     if (tri_in_chunk_max > 0)
-        k_raster_triangles<<<dim3(div_up(tri_in_chunk_max * 32, 256), frames), 256, 0, st>>>(rast, fp, max_tri, tri_map, w, h);
+        k_bin_fill<<<dim3(div_up(tri_in_chunk_max, 128), frames), 128, 0, st>>>(rast, fp, max_tri, img_w, img_h, tile_counts,
+                                                                              tile_off, overflow, tile_list, cap, tiles_x,
+                                                                              n_tiles);
 }
 
 }  // namespace poppy

@@ -1,21 +1,28 @@
 // Kernel group 3 — Laplacian-pyramid blend (reference src/blend.hpp:11-91) on planar float32 levels.
 //
 // Per frame and level k >= 1 the Gaussian pyramids are stored as 7 planes (left B,G,R, right B,G,R, mask); level 0
-// is never materialised in float: it is the warped 8-bit pair converted on the fly (src/algo.cpp:247-248) plus the
-// frame's mask evaluated from the pair's mask basis (src/algo.cpp:250-258). The collapsed result out[k] has 3 planes.
+// is never materialised in float for the images: it is the warped 8-bit pair converted on the fly
+// (src/algo.cpp:247-248). The level-0 blend mask (src/algo.cpp:250-258) is evaluated once, by the mask role of the
+// level 0 -> 1 kernel, and kept as a float plane for the level-0 collapse. The collapsed result out[k] has 3 planes.
 //
-//   k_pyr_down_tile   cv::pyrDown of one plane, 64x16 output tile per CTA: separable 1-4-6-4-1, the row pass goes
-//   k_pyr_down0_tile  through shared memory once             OCV imgproc/src/pyramids.cpp:745-900 (+344-402, 503-521)
-//   k_blend_coarsest  resultSmallest                         reference src/blend.hpp:68-69
-//   k_collapse_tile   lap = G - pyrUp(G_coarse) for both images, per-level blend, and
-//                     out = pyrUp(out_coarse) + blended, 128x32 fine tile per CTA; the polyphase row pass of the nine
-//                     coarse planes is staged in shared memory  reference src/blend.hpp:45-77; pyramids.cpp:903-1005
+//   k_pyr_down_roll    cv::pyrDown, level k -> k+1 of one plane   OCV imgproc/src/pyramids.cpp:745-900 (+344-402, 503-521)
+//   k_pyr_down0_roll   level 0 -> 1, one warp per role (the six colour planes of the two images | the mask)
+//   k_blend_coarsest   resultSmallest                             reference src/blend.hpp:68-69
+//   k_collapse_roll    lap = G - pyrUp(G_coarse) for both images, per-level blend, and out = pyrUp(out_coarse) + blended,
+//                      one warp per colour channel                reference src/blend.hpp:45-77; pyramids.cpp:903-1005
+//
+// Design (B200: the path is bound by instruction issue, not by HBM): no shared memory and no barriers.
+// A thread owns 4 adjacent output columns and walks down a run of rows; the separable filters keep their row-pass
+// results in a register window that slides with the walk, so every source row is filtered horizontally once per
+// thread column. Work that shares source pixels but not arithmetic (the colour channels / the two images / the mask)
+// is split across the warps of a CTA ("roles") so that the sliding windows stay small and the shared loads hit L1.
+// Every kernel body exists twice: an INTERIOR instantiation (no border logic at all, vector loads only, the
+// reference's vector-body association everywhere) and a generic one (cv::borderInterpolate on every tap, association
+// selected per element, any size down to 1x1); a warp picks one with a single uniform branch.
 //
 // Bit-exactness: OpenCV's SSE-baseline vector bodies associate the 5-tap sums differently from the scalar code
 // that handles row borders and loop tails, so the association is selected per element position exactly as the
-// reference loops do (hv/vv below); all adds and multiplies are individually rounded (no FMA contraction).
-// Tile interiors take vectorised fast paths; everything that touches an image border takes a scalar path with
-// cv::borderInterpolate semantics, so any size (down to 1x1 levels) is handled by the same kernels.
+// reference loops do (DownSel below); all adds and multiplies are individually rounded (no FMA contraction).
 #include "common.cuh"
 #include "kernels.cuh"
 #include "pixel_ops.cuh"
@@ -23,6 +30,8 @@
 namespace poppy {
 
 namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
 
 // horizontal 1-4-6-4-1, vector-body association: r2*6 + ((r1+r3)*4 + (r0+r4))
 __device__ __forceinline__ float h5_vec(float t0, float t1, float t2, float t3, float t4) {
@@ -32,9 +41,6 @@ __device__ __forceinline__ float h5_vec(float t0, float t1, float t2, float t3, 
 __device__ __forceinline__ float h5_sca(float t0, float t1, float t2, float t3, float t4) {
     return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t2, 6.f), __fmul_rn(__fadd_rn(t1, t3), 4.f)), t0), t4);
 }
-__device__ __forceinline__ float h5(bool vec, float t0, float t1, float t2, float t3, float t4) {
-    return vec ? h5_vec(t0, t1, t2, t3, t4) : h5_sca(t0, t1, t2, t3, t4);
-}
 // vertical, vector body: ((r1+r3+r2)*4 + (r0+r4+(r2+r2))) * 1/256
 __device__ __forceinline__ float v5_vec(float r0, float r1, float r2, float r3, float r4) {
     const float a = __fmul_rn(__fadd_rn(__fadd_rn(r1, r3), r2), 4.f);
@@ -43,9 +49,6 @@ __device__ __forceinline__ float v5_vec(float r0, float r1, float r2, float r3, 
 }
 __device__ __forceinline__ float v5_sca(float r0, float r1, float r2, float r3, float r4) {
     return __fmul_rn(h5_sca(r0, r1, r2, r3, r4), 1.f / 256);
-}
-__device__ __forceinline__ float v5(bool vec, float r0, float r1, float r2, float r3, float r4) {
-    return vec ? v5_vec(r0, r1, r2, r3, r4) : v5_sca(r0, r1, r2, r3, r4);
 }
 
 // Which output columns the reference's vector bodies produce (pyramids.cpp:380-402 cn=3, 344-360 cn=1, 503-521);
@@ -65,174 +68,253 @@ struct DownSel {
     __device__ __forceinline__ bool v1(int x) const { return x < v_end1; }
 };
 
-constexpr int PD_OW = 64, PD_OH = 16;        // output tile of the pyrDown kernels
-constexpr int PD_IR = 2 * PD_OH + 3;         // source rows a tile needs
+constexpr int DN_R = 16;          // output rows per warp of the pyrDown kernels (a warp covers 128 output columns)
 
-// Column pass of a pyrDown tile for one plane: thread (t, q) turns row-pass rows 4q..4q+6 of columns 2t, 2t+1 into
-// output rows oy0+2q, oy0+2q+1.
-__device__ __forceinline__ void down_column_pass(const float (*hs)[PD_OW], int tid, int ox0, int oy0, int dw, int dh,
-                                                 bool vec_a, bool vec_b, float* __restrict__ dplane, int dpitch) {
-    const int t = tid & 31, q = tid >> 5;
-    const int x = ox0 + 2 * t, y = oy0 + 2 * q;
-    if (x >= dw || y >= dh) return;
-    float2 hrow[7];
-    const int nrows = (y + 1 < dh) ? 7 : 5;
+// Per-thread association flags of the 4 output columns x..x+3 of one plane kind (bit i: vector-body association).
+struct DownFlags { unsigned h, v; };
+__device__ __forceinline__ DownFlags down_flags(const DownSel& sel, int x, bool three, int ch) {
+    DownFlags f{0u, 0u};
 #pragma unroll
-    for (int j = 0; j < 7; ++j)
-        if (j < nrows) hrow[j] = *reinterpret_cast<const float2*>(&hs[4 * q + j][2 * t]);
-    float2 o;
-    o.x = v5(vec_a, hrow[0].x, hrow[1].x, hrow[2].x, hrow[3].x, hrow[4].x);
-    o.y = v5(vec_b, hrow[0].y, hrow[1].y, hrow[2].y, hrow[3].y, hrow[4].y);
-    *reinterpret_cast<float2*>(dplane + (size_t)y * dpitch + x) = o;
-    if (nrows == 7) {
-        o.x = v5(vec_a, hrow[2].x, hrow[3].x, hrow[4].x, hrow[5].x, hrow[6].x);
-        o.y = v5(vec_b, hrow[2].y, hrow[3].y, hrow[4].y, hrow[5].y, hrow[6].y);
-        *reinterpret_cast<float2*>(dplane + (size_t)(y + 1) * dpitch + x) = o;
+    for (int i = 0; i < 4; ++i) {
+        if (three ? sel.h3(x + i) : sel.h1(x + i)) f.h |= 1u << i;
+        if (three ? sel.v3(x + i, ch) : sel.v1(x + i)) f.v |= 1u << i;
+    }
+    return f;
+}
+// Can this thread (output columns x..x+3 of a source row of sw pixels) run the INTERIOR body?
+__device__ __forceinline__ bool down_lane_interior(int x, int sw, int dw, DownFlags f) {
+    return x + 3 < dw && 2 * x - 2 >= 0 && 2 * x + 8 <= sw - 1 && f.h == 15u && f.v == 15u;
+}
+
+// row pass of the 4 outputs from the 11 taps s[2x-2 .. 2x+8]
+template <bool INTERIOR>
+__device__ __forceinline__ void h5x4(const float (&t)[11], unsigned hflags, float (&o)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        o[i] = (INTERIOR || ((hflags >> i) & 1u)) ? h5_vec(t[2 * i], t[2 * i + 1], t[2 * i + 2], t[2 * i + 3], t[2 * i + 4])
+                                                  : h5_sca(t[2 * i], t[2 * i + 1], t[2 * i + 2], t[2 * i + 3], t[2 * i + 4]);
+}
+template <bool INTERIOR>
+__device__ __forceinline__ float4 v5x4(const float (&r0)[4], const float (&r1)[4], const float (&r2)[4], const float (&r3)[4],
+                                       const float (&r4)[4], unsigned vflags) {
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        o[i] = (INTERIOR || ((vflags >> i) & 1u)) ? v5_vec(r0[i], r1[i], r2[i], r3[i], r4[i]) : v5_sca(r0[i], r1[i], r2[i], r3[i], r4[i]);
+    return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// ---- level k -> k+1, float planes -----------------------------------------------------------------------------------
+template <bool INTERIOR>
+__device__ __forceinline__ void down_row_f32(const float* __restrict__ plane, int spitch, int sw, int sh, int iy, int x,
+                                             unsigned hflags, float (&o)[4]) {
+    float t[11];
+    if (INTERIOR) {
+        const float* __restrict__ p = plane + (size_t)iy * spitch + 2 * x;
+        const float2 a = __ldg(reinterpret_cast<const float2*>(p - 2));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(p + 4));
+        t[0] = a.x; t[1] = a.y; t[2] = b.x; t[3] = b.y; t[4] = b.z; t[5] = b.w; t[6] = c.x; t[7] = c.y; t[8] = c.z; t[9] = c.w;
+        t[10] = __ldg(p + 8);
+    } else {
+        const float* __restrict__ row = plane + (size_t)reflect101(iy, sh) * spitch;
+#pragma unroll
+        for (int j = 0; j < 11; ++j) t[j] = __ldg(row + reflect101(2 * x - 2 + j, sw));
+    }
+    h5x4<INTERIOR>(t, hflags, o);
+}
+
+template <bool INTERIOR>
+__device__ __forceinline__ void down_body_f32(const float* __restrict__ sp, int sw, int sh, int spitch, float* __restrict__ dp,
+                                              int dh, int dpitch, int x, int y0, DownFlags fl) {
+    float h[7][4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) down_row_f32<INTERIOR>(sp, spitch, sw, sh, 2 * y0 - 2 + j, x, fl.h, h[j]);
+#pragma unroll 1
+    for (int k = 0; k < DN_R; k += 2) {
+        const int y = y0 + k;
+        if (!INTERIOR && y >= dh) break;
+        const bool two = INTERIOR || y + 1 < dh;
+        down_row_f32<INTERIOR>(sp, spitch, sw, sh, 2 * y + 1, x, fl.h, h[3]);
+        down_row_f32<INTERIOR>(sp, spitch, sw, sh, 2 * y + 2, x, fl.h, h[4]);
+        if (two) {
+            down_row_f32<INTERIOR>(sp, spitch, sw, sh, 2 * y + 3, x, fl.h, h[5]);
+            down_row_f32<INTERIOR>(sp, spitch, sw, sh, 2 * y + 4, x, fl.h, h[6]);
+        }
+        *reinterpret_cast<float4*>(dp + (size_t)y * dpitch + x) = v5x4<INTERIOR>(h[0], h[1], h[2], h[3], h[4], fl.v);
+        if (two) *reinterpret_cast<float4*>(dp + (size_t)(y + 1) * dpitch + x) = v5x4<INTERIOR>(h[2], h[3], h[4], h[5], h[6], fl.v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { h[0][i] = h[4][i]; h[1][i] = h[5][i]; h[2][i] = h[6][i]; }
     }
 }
 
 }  // namespace
 
-// ------------------------------------------------------------------------------------------------------------------
-// level k -> k+1 (k >= 1) of one plane. block 256; grid (ceil(dw/64), ceil(dh/16), frames * 7): blockIdx.z is the
-// plane job f*7+p, whose planes start at job * stride in both levels.
-__global__ void __launch_bounds__(256)
-k_pyr_down_tile(const float* __restrict__ src, int sw, int sh, int spitch, size_t sstride, float* __restrict__ dst, int dw,
+// block (32, 4); grid (ceil(dw/128), ceil(dh/64), frames * 7): blockIdx.z is the plane job f*7+p, whose planes start
+// at job * stride in both levels. Warp wy of a CTA produces output rows (blockIdx.y*4 + wy)*16 .. +15.
+__global__ void __launch_bounds__(128)
+k_pyr_down_roll(const float* __restrict__ src, int sw, int sh, int spitch, size_t sstride, float* __restrict__ dst, int dw,
                 int dh, int dpitch, size_t dstride) {
-    __shared__ __align__(16) float hs[PD_IR][PD_OW];
     const int job = blockIdx.z, p = job % 7;
+    const int x = blockIdx.x * 128 + 4 * threadIdx.x, y0 = (blockIdx.y * 4 + threadIdx.y) * DN_R;
+    if (y0 >= dh) return;
     const float* __restrict__ sp = src + (size_t)job * sstride;
     float* __restrict__ dp = dst + (size_t)job * dstride;
-    const int ox0 = blockIdx.x * PD_OW, oy0 = blockIdx.y * PD_OH;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const DownSel sel(sw, dw);
-    const bool three = p < 6;
-
-    // row pass: one warp per source row, lane -> output columns x, x+1 (taps 2x-2 .. 2x+4)
-    const int last_row = 2 * (min(oy0 + PD_OH, dh) - 1) + 2 - (2 * oy0 - 2);      // last needed row-pass row
-    const int x = ox0 + 2 * lane;
-    const bool va = three ? sel.h3(x) : sel.h1(x), vb = three ? sel.h3(x + 1) : sel.h1(x + 1);
-    for (int r = warp; r <= last_row; r += 8) {
-        const float* __restrict__ row = sp + (size_t)reflect101(2 * oy0 - 2 + r, sh) * spitch;
-        float2 o = make_float2(0.f, 0.f);
-        if (x < dw) {
-            const int c0 = 2 * x - 2;
-            if (c0 >= 0 && c0 + 6 < sw) {
-                const float2 a = __ldg(reinterpret_cast<const float2*>(row + c0));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(row + c0 + 2));
-                const float c = __ldg(row + c0 + 6);
-                o.x = h5(va, a.x, a.y, b.x, b.y, b.z);
-                o.y = h5(vb, b.x, b.y, b.z, b.w, c);
-            } else {
-                float t[5];
-#pragma unroll
-                for (int j = 0; j < 5; ++j) t[j] = __ldg(row + reflect101(c0 + j, sw));
-                o.x = h5(va, t[0], t[1], t[2], t[3], t[4]);
-                if (x + 1 < dw) {
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) t[j] = __ldg(row + reflect101(c0 + 2 + j, sw));
-                    o.y = h5(vb, t[0], t[1], t[2], t[3], t[4]);
-                }
-            }
-        }
-        *reinterpret_cast<float2*>(&hs[r][2 * lane]) = o;
+    const DownFlags fl = down_flags(sel, x, p < 6, p % 3);
+    const bool rows_in = 2 * y0 - 2 >= 0 && 2 * (y0 + DN_R - 1) + 2 <= sh - 1 && y0 + DN_R <= dh;
+    if (__all_sync(FULL, rows_in && down_lane_interior(x, sw, dw, fl))) {
+        down_body_f32<true>(sp, sw, sh, spitch, dp, dh, dpitch, x, y0, fl);
+    } else if (x < dw) {
+        down_body_f32<false>(sp, sw, sh, spitch, dp, dh, dpitch, x, y0, fl);
     }
-    __syncthreads();
-    const int xo = ox0 + 2 * (tid & 31);
-    const bool wa = three ? sel.v3(xo, p % 3) : sel.v1(xo), wb = three ? sel.v3(xo + 1, p % 3) : sel.v1(xo + 1);
-    down_column_pass(hs, tid, ox0, oy0, dw, dh, wa, wb, dp, dpitch);
 }
 
-// level 0 -> 1, all seven planes of a frame: the source is the warped 8-bit pair (one uint2 per pixel: image 1 BGR
-// in .x, image 2 BGR in .y) converted on the fly, and the frame's blend mask evaluated from the mask basis.
-// block 256; grid (ceil(dw/64), ceil(dh/16), frames); dynamic shared memory 7 * PD_IR * PD_OW floats.
-__global__ void __launch_bounds__(256)
-k_pyr_down0_tile(const uint2* __restrict__ warped, int wpitch, const float* __restrict__ basis, int bpitch,
-                 const FrameParams* __restrict__ fp, int sw, int sh, float* __restrict__ dst, int dw, int dh, int dpitch,
-                 size_t dstride) {
-    extern __shared__ __align__(16) float smem_dyn[];
-    float (*hs)[PD_IR][PD_OW] = reinterpret_cast<float (*)[PD_IR][PD_OW]>(smem_dyn);
-    const int f = blockIdx.z;
-    const int ox0 = blockIdx.x * PD_OW, oy0 = blockIdx.y * PD_OH;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const DownSel sel(sw, dw);
-    const double alpha = fp[f].mask_alpha, beta = fp[f].mask_beta;
-    const uint2* __restrict__ wframe = warped + (size_t)f * sh * wpitch;
+// ---- level 0 -> 1 -----------------------------------------------------------------------------------------------------
+namespace {
 
-    const int last_row = 2 * (min(oy0 + PD_OH, dh) - 1) + 2 - (2 * oy0 - 2);
-    const int x = ox0 + 2 * lane;
-    const bool va3 = sel.h3(x), vb3 = sel.h3(x + 1), va1 = sel.h1(x), vb1 = sel.h1(x + 1);
-    for (int r = warp; r <= last_row; r += 8) {
-        const int sy = reflect101(2 * oy0 - 2 + r, sh);
-        const uint2* __restrict__ wrow = wframe + (size_t)sy * wpitch;
-        const float* __restrict__ brow = basis + (size_t)sy * bpitch;
-        if (x >= dw) continue;          // columns past the level: never read by the column pass
-        const int c0 = 2 * x - 2;
-        if (c0 >= 0 && c0 + 6 < sw) {
-            uint32_t lo[7], hi[7];
-            float mk[7];
-            {
-                const uint4 a = __ldg(reinterpret_cast<const uint4*>(wrow + c0));
-                const uint4 b = __ldg(reinterpret_cast<const uint4*>(wrow + c0 + 2));
-                const uint4 c = __ldg(reinterpret_cast<const uint4*>(wrow + c0 + 4));
-                const uint2 d = __ldg(wrow + c0 + 6);
-                lo[0] = a.x; hi[0] = a.y; lo[1] = a.z; hi[1] = a.w;
-                lo[2] = b.x; hi[2] = b.y; lo[3] = b.z; hi[3] = b.w;
-                lo[4] = c.x; hi[4] = c.y; lo[5] = c.z; hi[5] = c.w;
-                lo[6] = d.x; hi[6] = d.y;
-                const float2 ma = __ldg(reinterpret_cast<const float2*>(brow + c0));
-                const float4 mb = __ldg(reinterpret_cast<const float4*>(brow + c0 + 2));
-                const float mc = __ldg(brow + c0 + 6);
-                mk[0] = blend_mask(ma.x, alpha, beta); mk[1] = blend_mask(ma.y, alpha, beta);
-                mk[2] = blend_mask(mb.x, alpha, beta); mk[3] = blend_mask(mb.y, alpha, beta);
-                mk[4] = blend_mask(mb.z, alpha, beta); mk[5] = blend_mask(mb.w, alpha, beta);
-                mk[6] = blend_mask(mc, alpha, beta);
-            }
+// 11 source pixels 2x-2 .. 2x+8 of one warped row: the packed BGR word of image IMG (0: .x, 1: .y) of each
+template <bool INTERIOR, int IMG>
+__device__ __forceinline__ void load_words11(const uint2* __restrict__ wframe, int wpitch, int sw, int sh, int iy, int x,
+                                             uint32_t (&wd)[11]) {
+    if (INTERIOR) {
+        const uint2* __restrict__ p = wframe + (size_t)iy * wpitch + 2 * x;
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p - 2));
+        wd[0] = IMG ? a.y : a.x; wd[1] = IMG ? a.w : a.z;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float t[7];
+        for (int j = 0; j < 4; ++j) {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p + 2 * j));
+            wd[2 + 2 * j] = IMG ? b.y : b.x; wd[3 + 2 * j] = IMG ? b.w : b.z;
+        }
+        const uint2 c = __ldg(p + 8);
+        wd[10] = IMG ? c.y : c.x;
+    } else {
+        const uint2* __restrict__ row = wframe + (size_t)reflect101(iy, sh) * wpitch;
 #pragma unroll
-                for (int j = 0; j < 7; ++j) t[j] = unit_from_byte(lo[j], c);
-                *reinterpret_cast<float2*>(&hs[c][r][2 * lane]) =
-                    make_float2(h5(va3, t[0], t[1], t[2], t[3], t[4]), h5(vb3, t[2], t[3], t[4], t[5], t[6]));
-#pragma unroll
-                for (int j = 0; j < 7; ++j) t[j] = unit_from_byte(hi[j], c);
-                *reinterpret_cast<float2*>(&hs[3 + c][r][2 * lane]) =
-                    make_float2(h5(va3, t[0], t[1], t[2], t[3], t[4]), h5(vb3, t[2], t[3], t[4], t[5], t[6]));
-            }
-            *reinterpret_cast<float2*>(&hs[6][r][2 * lane]) =
-                make_float2(h5(va1, mk[0], mk[1], mk[2], mk[3], mk[4]), h5(vb1, mk[2], mk[3], mk[4], mk[5], mk[6]));
-        } else {
-#pragma unroll 1
-            for (int i = 0; i < 2; ++i) {
-                if (x + i >= dw) break;
-                const bool v3 = i ? vb3 : va3, v1 = i ? vb1 : va1;
-                uint32_t lo[5], hi[5];
-                float mk[5];
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const int cx = reflect101(c0 + 2 * i + j, sw);
-                    const uint2 px = __ldg(wrow + cx);
-                    lo[j] = px.x; hi[j] = px.y;
-                    mk[j] = blend_mask(__ldg(brow + cx), alpha, beta);
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    hs[c][r][2 * lane + i] = h5(v3, unit_from_byte(lo[0], c), unit_from_byte(lo[1], c), unit_from_byte(lo[2], c),
-                                                unit_from_byte(lo[3], c), unit_from_byte(lo[4], c));
-                    hs[3 + c][r][2 * lane + i] = h5(v3, unit_from_byte(hi[0], c), unit_from_byte(hi[1], c), unit_from_byte(hi[2], c),
-                                                    unit_from_byte(hi[3], c), unit_from_byte(hi[4], c));
-                }
-                hs[6][r][2 * lane + i] = h5(v1, mk[0], mk[1], mk[2], mk[3], mk[4]);
-            }
+        for (int j = 0; j < 11; ++j) {
+            const uint2 q = __ldg(row + reflect101(2 * x - 2 + j, sw));
+            wd[j] = IMG ? q.y : q.x;
         }
     }
-    __syncthreads();
-    const int xo = ox0 + 2 * (tid & 31);
+}
+
+// roles 0..5: colour plane c of image IMG
+template <bool INTERIOR, int IMG>
+__device__ __forceinline__ void down0_body_img(const uint2* __restrict__ wframe, int wpitch, int sw, int sh, int c,
+                                               float* __restrict__ dp /* plane 3*IMG + c of the frame */, int dh, int dpitch,
+                                               int x, int y0, DownFlags fl) {
+    float h[7][4];
+    auto row = [&](int iy, int slot) {
+        uint32_t wd[11];
+        load_words11<INTERIOR, IMG>(wframe, wpitch, sw, sh, iy, x, wd);
+        float t[11];
+#pragma unroll
+        for (int j = 0; j < 11; ++j) t[j] = unit_from_byte(wd[j], c);
+        h5x4<INTERIOR>(t, fl.h, h[slot]);
+    };
+    row(2 * y0 - 2, 0); row(2 * y0 - 1, 1); row(2 * y0, 2);
 #pragma unroll 1
-    for (int p = 0; p < 7; ++p) {
-        const bool wa = p < 6 ? sel.v3(xo, p % 3) : sel.v1(xo), wb = p < 6 ? sel.v3(xo + 1, p % 3) : sel.v1(xo + 1);
-        down_column_pass(hs[p], tid, ox0, oy0, dw, dh, wa, wb, dst + ((size_t)f * 7 + p) * dstride, dpitch);
+    for (int k = 0; k < DN_R; k += 2) {
+        const int y = y0 + k;
+        if (!INTERIOR && y >= dh) break;
+        const bool two = INTERIOR || y + 1 < dh;
+        row(2 * y + 1, 3); row(2 * y + 2, 4);
+        if (two) { row(2 * y + 3, 5); row(2 * y + 4, 6); }
+        float* __restrict__ o = dp + (size_t)y * dpitch + x;
+        *reinterpret_cast<float4*>(o) = v5x4<INTERIOR>(h[0], h[1], h[2], h[3], h[4], fl.v);
+        if (two) *reinterpret_cast<float4*>(o + dpitch) = v5x4<INTERIOR>(h[2], h[3], h[4], h[5], h[6], fl.v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { h[0][i] = h[4][i]; h[1][i] = h[5][i]; h[2][i] = h[6][i]; }
+    }
+}
+
+// role 6: the blend mask — evaluates lbmask from the mask basis, keeps it as the level-0 mask plane (own rows and
+// columns only) and reduces it to level 1
+template <bool INTERIOR>
+__device__ __forceinline__ void down0_body_mask(const float* __restrict__ basis, int bpitch, double alpha, double beta, int sw,
+                                                int sh, float* __restrict__ mask0, float* __restrict__ dp, int dh, int dpitch,
+                                                int x, int y0, DownFlags fl) {
+    float h[7][4];
+    auto row = [&](int iy, int slot) {
+        float t[11];
+        if (INTERIOR) {
+            const float* __restrict__ p = basis + (size_t)iy * bpitch + 2 * x;
+            const float2 a = __ldg(reinterpret_cast<const float2*>(p - 2));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(p + 4));
+            t[0] = a.x; t[1] = a.y; t[2] = b.x; t[3] = b.y; t[4] = b.z; t[5] = b.w; t[6] = c.x; t[7] = c.y; t[8] = c.z; t[9] = c.w;
+            t[10] = __ldg(p + 8);
+        } else {
+            const float* __restrict__ r = basis + (size_t)reflect101(iy, sh) * bpitch;
+#pragma unroll
+            for (int j = 0; j < 11; ++j) t[j] = __ldg(r + reflect101(2 * x - 2 + j, sw));
+        }
+#pragma unroll
+        for (int j = 0; j < 11; ++j) t[j] = blend_mask(t[j], alpha, beta);
+        // level-0 mask plane: this thread owns source columns 2x .. 2x+7 of the source rows 2*y0 .. 2*y0 + 2*DN_R - 1
+        if (iy >= 2 * y0 && iy < 2 * y0 + 2 * DN_R && (INTERIOR || iy < sh)) {
+            float* __restrict__ m = mask0 + (size_t)iy * bpitch + 2 * x;
+            if (INTERIOR || 2 * x + 7 < sw) {
+                *reinterpret_cast<float4*>(m) = make_float4(t[2], t[3], t[4], t[5]);
+                *reinterpret_cast<float4*>(m + 4) = make_float4(t[6], t[7], t[8], t[9]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (2 * x + j < sw) m[j] = t[2 + j];
+            }
+        }
+        h5x4<INTERIOR>(t, fl.h, h[slot]);
+    };
+    row(2 * y0 - 2, 0); row(2 * y0 - 1, 1); row(2 * y0, 2);
+#pragma unroll 1
+    for (int k = 0; k < DN_R; k += 2) {
+        const int y = y0 + k;
+        if (!INTERIOR && y >= dh) break;
+        const bool two = INTERIOR || y + 1 < dh;
+        row(2 * y + 1, 3); row(2 * y + 2, 4);
+        if (two) { row(2 * y + 3, 5); row(2 * y + 4, 6); }
+        float* __restrict__ o = dp + (size_t)y * dpitch + x;
+        *reinterpret_cast<float4*>(o) = v5x4<INTERIOR>(h[0], h[1], h[2], h[3], h[4], fl.v);
+        if (two) *reinterpret_cast<float4*>(o + dpitch) = v5x4<INTERIOR>(h[2], h[3], h[4], h[5], h[6], fl.v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { h[0][i] = h[4][i]; h[1][i] = h[5][i]; h[2][i] = h[6][i]; }
+    }
+}
+
+}  // namespace
+
+// block (32, 7): warp = role (0-2: image 1 B,G,R; 3-5: image 2 B,G,R; 6: mask); grid (ceil(dw/128), ceil(dh/16), frames).
+// warped: one uint2 per pixel (image 1 BGR in .x, image 2 BGR in .y), rows wpitch pixels apart. mask0: per-frame
+// level-0 mask planes (rows bpitch floats apart, plane stride m0stride) written here for k_collapse_roll<true>.
+__global__ void __launch_bounds__(224)
+k_pyr_down0_roll(const uint2* __restrict__ warped, int wpitch, const float* __restrict__ basis, int bpitch,
+                 const FrameParams* __restrict__ fp, int sw, int sh, float* __restrict__ mask0, size_t m0stride,
+                 float* __restrict__ dst, int dw, int dh, int dpitch, size_t dstride) {
+    const int f = blockIdx.z, role = threadIdx.y;
+    const int x = blockIdx.x * 128 + 4 * threadIdx.x, y0 = blockIdx.y * DN_R;
+    const DownSel sel(sw, dw);
+    const bool rows_in = 2 * y0 - 2 >= 0 && 2 * (y0 + DN_R - 1) + 2 <= sh - 1 && y0 + DN_R <= dh;
+    float* __restrict__ dp = dst + ((size_t)f * 7 + role) * dstride;
+    if (role < 6) {
+        const int c = role % 3;
+        const DownFlags fl = down_flags(sel, x, true, c);
+        const uint2* __restrict__ wframe = warped + (size_t)f * sh * wpitch;
+        const bool interior = __all_sync(FULL, rows_in && down_lane_interior(x, sw, dw, fl));
+        if (role < 3) {
+            if (interior) down0_body_img<true, 0>(wframe, wpitch, sw, sh, c, dp, dh, dpitch, x, y0, fl);
+            else if (x < dw) down0_body_img<false, 0>(wframe, wpitch, sw, sh, c, dp, dh, dpitch, x, y0, fl);
+        } else {
+            if (interior) down0_body_img<true, 1>(wframe, wpitch, sw, sh, c, dp, dh, dpitch, x, y0, fl);
+            else if (x < dw) down0_body_img<false, 1>(wframe, wpitch, sw, sh, c, dp, dh, dpitch, x, y0, fl);
+        }
+    } else {
+        const DownFlags fl = down_flags(sel, x, false, 0);
+        const double alpha = fp[f].mask_alpha, beta = fp[f].mask_beta;
+        float* __restrict__ m0 = mask0 + (size_t)f * m0stride;
+        if (__all_sync(FULL, rows_in && down_lane_interior(x, sw, dw, fl)))
+            down0_body_mask<true>(basis, bpitch, alpha, beta, sw, sh, m0, dp, dh, dpitch, x, y0, fl);
+        else if (x < dw)
+            down0_body_mask<false>(basis, bpitch, alpha, beta, sw, sh, m0, dp, dh, dpitch, x, y0, fl);
     }
 }
 
@@ -250,12 +332,10 @@ __global__ void k_blend_coarsest(const float* __restrict__ g, int w, int h, int 
             __fadd_rn(__fmul_rn(gf[(size_t)c * stride], m), __fmul_rn(gf[(size_t)(3 + c) * stride], anti));
 }
 
-// ------------------------------------------------------------------------------------------------------------------
+// ---- collapse ---------------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int CT_FW = 128, CT_FH = 32;                 // fine tile of the collapse kernel
-constexpr int CT_HR = CT_FH / 2 + 2;                   // coarse rows cy0-1 .. cy0+CT_FH/2 take part
-constexpr size_t CT_SMEM = (size_t)9 * CT_HR * CT_FW * sizeof(float);
+constexpr int CL_R = 16;           // coarse rows per warp of the collapse kernel (32 fine rows x 128 fine columns)
 
 // horizontal pass of cv::pyrUp at fine column x of one coarse row of n pixels (pyramids.cpp:945-978)
 __device__ __forceinline__ float up_h(const float* __restrict__ row, int n, int x) {
@@ -270,185 +350,154 @@ __device__ __forceinline__ float up_h(const float* __restrict__ row, int n, int 
     return __fadd_rn(__fadd_rn(__ldg(row + sx - 1), __fmul_rn(__ldg(row + sx), 6.f)), __ldg(row + sx + 1));
 }
 
-// vertical pass of cv::pyrUp (pyramids.cpp:929-993): even fine row (r0 + 6 r1 + r2)/64, odd fine row 4 (r1 + r2)/64
+// Row pass of cv::pyrUp for the 4 fine columns fx..fx+3 (coarse columns a = fx/2, a+1) of one coarse row, scaled by 1/64.
+// Scaling by a power of two is exact and commutes with every rounding of the column pass, so applying it here instead of
+// after the column sums (pyramids.cpp:989-991) is bit-identical and saves one multiply per value and fine row.
+template <bool INTERIOR>
+__device__ __forceinline__ void up_row(const float* __restrict__ row, int cw, int w, int fx, float (&o)[4]) {
+    if (INTERIOR) {
+        const float* __restrict__ p = row + (fx >> 1);
+        const float cm = __ldg(p - 1);
+        const float2 c01 = __ldg(reinterpret_cast<const float2*>(p));
+        const float cp = __ldg(p + 2);
+        o[0] = __fadd_rn(__fadd_rn(cm, __fmul_rn(c01.x, 6.f)), c01.y);
+        o[1] = __fmul_rn(__fadd_rn(c01.x, c01.y), 4.f);
+        o[2] = __fadd_rn(__fadd_rn(c01.x, __fmul_rn(c01.y, 6.f)), cp);
+        o[3] = __fmul_rn(__fadd_rn(c01.y, cp), 4.f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = fx + i < w ? up_h(row, cw, fx + i) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __fmul_rn(o[i], 1.f / 64);
+}
+
+// vertical pass of cv::pyrUp (pyramids.cpp:929-993) on pre-scaled row-pass values:
+// even fine row (r0 + 6 r1) + r2, odd fine row (r1 + r2) * 4
 __device__ __forceinline__ float up_even(float h0, float h1, float h2) {
-    return __fmul_rn(__fadd_rn(__fadd_rn(h0, __fmul_rn(h1, 6.f)), h2), 1.f / 64);
+    return __fadd_rn(__fadd_rn(h0, __fmul_rn(h1, 6.f)), h2);
 }
-__device__ __forceinline__ float up_odd(float h1, float h2) {
-    return __fmul_rn(__fmul_rn(__fadd_rn(h1, h2), 4.f), 1.f / 64);
+__device__ __forceinline__ float up_odd(float h1, float h2) { return __fmul_rn(__fadd_rn(h1, h2), 4.f); }
+
+// out = up_o + ((gl - up_l) * m + (gr - up_r) * (1 - m))        (blend.hpp:52-53,70-72,62-63)
+__device__ __forceinline__ float blend1(float gl, float gr, float m, float ul, float ur, float uo) {
+    const float lap_l = __fsub_rn(gl, ul), lap_r = __fsub_rn(gr, ur);
+    return __fadd_rn(uo, __fadd_rn(__fmul_rn(lap_l, m), __fmul_rn(lap_r, __fsub_rn(1.f, m))));
 }
 
-struct Up4x4 { float4 row[4]; };     // pyrUp values of a 4-column x 4-row fine block
+struct CollapseArgs {
+    // fine level: L0 -> warped pair + level-0 mask plane; else the 7 Gaussian planes
+    const uint2* wframe; int wpitch;
+    const float* mask0; int mpitch;
+    const float* gfine; int fpitch; size_t fstride;
+    // coarse level
+    const float* gc; const float* oc; int cw, ch, cpitch; size_t cstride;
+    float* out; int opitch; size_t ostride;
+    int w, h;
+};
 
-// Fine rows 4q..4q+3 of the tile come from coarse rows sy0 = cy0+2q and sy0+1; ja..jd are the shared-memory rows of
-// (sy0-1 | reflected), sy0, sy0+1 (clamped), sy0+2 (clamped) for this plane.
-__device__ __forceinline__ Up4x4 up_block(const float* __restrict__ hp, int col, int ja, int jb, int jc, int jd) {
-    const float4 a = *reinterpret_cast<const float4*>(hp + ja * CT_FW + col);
-    const float4 b = *reinterpret_cast<const float4*>(hp + jb * CT_FW + col);
-    const float4 c = *reinterpret_cast<const float4*>(hp + jc * CT_FW + col);
-    const float4 d = *reinterpret_cast<const float4*>(hp + jd * CT_FW + col);
-    Up4x4 u;
-    u.row[0] = make_float4(up_even(a.x, b.x, c.x), up_even(a.y, b.y, c.y), up_even(a.z, b.z, c.z), up_even(a.w, b.w, c.w));
-    u.row[1] = make_float4(up_odd(b.x, c.x), up_odd(b.y, c.y), up_odd(b.z, c.z), up_odd(b.w, c.w));
-    u.row[2] = make_float4(up_even(b.x, c.x, d.x), up_even(b.y, c.y, d.y), up_even(b.z, c.z, d.z), up_even(b.w, c.w, d.w));
-    u.row[3] = make_float4(up_odd(c.x, d.x), up_odd(c.y, d.y), up_odd(c.z, d.z), up_odd(c.w, d.w));
-    return u;
+// One warp = one colour channel c of a 128 x 32 fine tile.
+template <bool L0, bool INTERIOR>
+__device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int fx, int cy0) {
+    const float* __restrict__ pl = A.gc + (size_t)c * A.cstride;
+    const float* __restrict__ pr = A.gc + (size_t)(3 + c) * A.cstride;
+    const float* __restrict__ po = A.oc + (size_t)c * A.cstride;
+    float hm[3][4], h0[3][4], hp[3][4];          // row-pass values of coarse rows sy-1, sy, sy+1 for (left, right, out)
+    auto rows3 = [&](int cy, float (&h)[3][4]) {
+        const size_t off = (size_t)cy * A.cpitch;
+        up_row<INTERIOR>(pl + off, A.cw, A.w, fx, h[0]);
+        up_row<INTERIOR>(pr + off, A.cw, A.w, fx, h[1]);
+        up_row<INTERIOR>(po + off, A.cw, A.w, fx, h[2]);
+    };
+    // borderInterpolate(2(sy-1), 2ch, REFLECT_101)/2: row -1 -> 1 (0 when the level has a single row)
+    rows3(INTERIOR ? cy0 - 1 : (cy0 >= 1 ? cy0 - 1 : (A.ch > 1 ? 1 : 0)), hm);
+    rows3(cy0, h0);
+    float* __restrict__ orow = A.out + (size_t)c * A.ostride + (size_t)(2 * cy0) * A.opitch + fx;
+#pragma unroll 1
+    for (int k = 0; k < CL_R; ++k) {
+        const int sy = cy0 + k, fy = 2 * sy;
+        if (!INTERIOR && fy >= A.h) break;
+        rows3(INTERIOR ? sy + 1 : min(sy + 1, A.ch - 1), hp);
+        const bool two = INTERIOR || fy + 1 < A.h;
+        // fine Gaussian values of this channel and the mask, rows fy and fy+1
+        float gl[2][4], gr[2][4], mk[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (r == 1 && !two) break;
+            if (L0) {
+                const uint2* __restrict__ wp = A.wframe + (size_t)(fy + r) * A.wpitch + fx;
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(wp)), b = __ldg(reinterpret_cast<const uint4*>(wp + 2));
+                gl[r][0] = unit_from_byte(a.x, c); gl[r][1] = unit_from_byte(a.z, c);
+                gl[r][2] = unit_from_byte(b.x, c); gl[r][3] = unit_from_byte(b.z, c);
+                gr[r][0] = unit_from_byte(a.y, c); gr[r][1] = unit_from_byte(a.w, c);
+                gr[r][2] = unit_from_byte(b.y, c); gr[r][3] = unit_from_byte(b.w, c);
+                const float4 m = __ldg(reinterpret_cast<const float4*>(A.mask0 + (size_t)(fy + r) * A.mpitch + fx));
+                mk[r][0] = m.x; mk[r][1] = m.y; mk[r][2] = m.z; mk[r][3] = m.w;
+            } else {
+                const float* __restrict__ gp = A.gfine + (size_t)(fy + r) * A.fpitch + fx;
+                const float4 l = __ldg(reinterpret_cast<const float4*>(gp + (size_t)c * A.fstride));
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(gp + (size_t)(3 + c) * A.fstride));
+                const float4 m = __ldg(reinterpret_cast<const float4*>(gp + (size_t)6 * A.fstride));
+                gl[r][0] = l.x; gl[r][1] = l.y; gl[r][2] = l.z; gl[r][3] = l.w;
+                gr[r][0] = rr.x; gr[r][1] = rr.y; gr[r][2] = rr.z; gr[r][3] = rr.w;
+                mk[r][0] = m.x; mk[r][1] = m.y; mk[r][2] = m.z; mk[r][3] = m.w;
+            }
+        }
+        float e[4], o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            e[i] = blend1(gl[0][i], gr[0][i], mk[0][i], up_even(hm[0][i], h0[0][i], hp[0][i]), up_even(hm[1][i], h0[1][i], hp[1][i]),
+                          up_even(hm[2][i], h0[2][i], hp[2][i]));
+            if (two)
+                o[i] = blend1(gl[1][i], gr[1][i], mk[1][i], up_odd(h0[0][i], hp[0][i]), up_odd(h0[1][i], hp[1][i]),
+                              up_odd(h0[2][i], hp[2][i]));
+        }
+        *reinterpret_cast<float4*>(orow) = make_float4(e[0], e[1], e[2], e[3]);
+        if (two) *reinterpret_cast<float4*>(orow + A.opitch) = make_float4(o[0], o[1], o[2], o[3]);
+        orow += 2 * (size_t)A.opitch;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { hm[p][i] = h0[p][i]; h0[p][i] = hp[p][i]; }
+    }
 }
 
 }  // namespace
 
-// block 256; grid (ceil(w/128), ceil(h/32), frames); dynamic shared memory CT_SMEM.
-// L0: the fine Gaussian level is the warped 8-bit pair + mask basis (see k_pyr_down0_tile); else g_fine (7 planes).
+// block (32, 3): warp = colour channel; grid (ceil(w/128), ceil(h/32), frames).
+// L0: the fine Gaussian level is the warped 8-bit pair + the level-0 mask plane written by k_pyr_down0_roll.
 template <bool L0>
-__global__ void __launch_bounds__(256, 2)
-k_collapse_tile(const uint2* __restrict__ warped, int wpitch, const float* __restrict__ basis, int bpitch,
-                const FrameParams* __restrict__ fp, const float* __restrict__ g_fine, int w, int h, int fpitch,
-                size_t fstride, const float* __restrict__ g_coarse, const float* __restrict__ out_coarse, int cw, int ch,
-                int cpitch, size_t cstride, float* __restrict__ out_fine, int opitch, size_t ostride) {
-    extern __shared__ __align__(16) float smem_dyn[];
-    float* hs = smem_dyn;                                   // [9][CT_HR][CT_FW]
-    const int f = blockIdx.z;
-    const int fx0 = blockIdx.x * CT_FW, fy0 = blockIdx.y * CT_FH;
-    const int cx0 = fx0 >> 1, cy0 = fy0 >> 1;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float* __restrict__ gc = g_coarse + (size_t)f * 7 * cstride;
-    const float* __restrict__ oc = out_coarse + (size_t)f * 3 * cstride;
-
-    // 1) polyphase row pass of the nine coarse planes: one warp per (plane, coarse row); lane -> 4 fine columns
-    {
-        const int fx = fx0 + 4 * lane, a = cx0 + 2 * lane;
-        const bool interior = a >= 1 && a + 2 <= cw - 1;
-        for (int task = warp; task < 9 * CT_HR; task += 8) {
-            const int p = task / CT_HR, j = task - p * CT_HR;
-            const int cy = cy0 - 1 + j;
-            if (cy < 0 || cy >= ch || fx >= w) continue;
-            const float* __restrict__ row = (p < 6 ? gc + (size_t)p * cstride : oc + (size_t)(p - 6) * cstride) + (size_t)cy * cpitch;
-            float4 o;
-            if (interior) {
-                const float cm = __ldg(row + a - 1);
-                const float2 c01 = __ldg(reinterpret_cast<const float2*>(row + a));
-                const float cp = __ldg(row + a + 2);
-                o.x = __fadd_rn(__fadd_rn(cm, __fmul_rn(c01.x, 6.f)), c01.y);
-                o.y = __fmul_rn(__fadd_rn(c01.x, c01.y), 4.f);
-                o.z = __fadd_rn(__fadd_rn(c01.x, __fmul_rn(c01.y, 6.f)), cp);
-                o.w = __fmul_rn(__fadd_rn(c01.y, cp), 4.f);
-            } else {
-                o.x = up_h(row, cw, fx);
-                o.y = fx + 1 < w ? up_h(row, cw, fx + 1) : 0.f;
-                o.z = fx + 2 < w ? up_h(row, cw, fx + 2) : 0.f;
-                o.w = fx + 3 < w ? up_h(row, cw, fx + 3) : 0.f;
-            }
-            *reinterpret_cast<float4*>(hs + ((size_t)p * CT_HR + j) * CT_FW + 4 * lane) = o;
-        }
-    }
-    __syncthreads();
-
-    // 2) column pass + blend: thread -> fine columns fx..fx+3, fine rows fy..fy+3 (coarse rows sy0, sy0+1)
-    const int q = warp;
-    const int fx = fx0 + 4 * lane, fy = fy0 + 4 * q;
-    if (fx >= w || fy >= h) return;
-    const int sy0 = cy0 + 2 * q;
-    // shared-memory row of coarse row r is r - cy0 + 1
-    const int jb = 2 * q + 1;                                                   // sy0
-    const int ja = sy0 >= 1 ? jb - 1 : (ch > 1 ? 1 - cy0 + 1 : jb);              // borderInterpolate(2(sy0-1), 2ch)/2
-    const int jc = min(sy0 + 1, ch - 1) - cy0 + 1;
-    const int jd = min(sy0 + 2, ch - 1) - cy0 + 1;
-    const int rows = min(4, h - fy);
-
-    float4 mk[4];                      // the mask is shared by the three channels
-    uint4 w01[4], w23[4];
-    if (L0) {
-        const double alpha = fp[f].mask_alpha, beta = fp[f].mask_beta;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (i < rows) {
-                const uint2* __restrict__ wrow = warped + ((size_t)f * h + fy + i) * wpitch + fx;
-                w01[i] = __ldg(reinterpret_cast<const uint4*>(wrow));
-                w23[i] = __ldg(reinterpret_cast<const uint4*>(wrow + 2));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(basis + (size_t)(fy + i) * bpitch + fx));
-                mk[i] = make_float4(blend_mask(b.x, alpha, beta), blend_mask(b.y, alpha, beta),
-                                    blend_mask(b.z, alpha, beta), blend_mask(b.w, alpha, beta));
-            }
-        }
-    } else {
-        const float* __restrict__ mp = g_fine + ((size_t)f * 7 + 6) * fstride + (size_t)fy * fpitch + fx;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (i < rows) mk[i] = __ldg(reinterpret_cast<const float4*>(mp + (size_t)i * fpitch));
-    }
-
-#pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
-        // acc = (gl - up_l) * m, then += (gr - up_r) * (1 - m), then out = up_o + acc      (blend.hpp:52-53,70-72,62-63)
-        float4 acc[4];
-        const float* __restrict__ lp = L0 ? nullptr : g_fine + ((size_t)f * 7 + c) * fstride + (size_t)fy * fpitch + fx;
-        {
-            const Up4x4 u = up_block(hs + (size_t)c * CT_HR * CT_FW, 4 * lane, ja, jb, jc, jd);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i < rows) {
-                    float4 g;
-                    if (L0) g = make_float4(unit_from_byte(w01[i].x, c), unit_from_byte(w01[i].z, c), unit_from_byte(w23[i].x, c),
-                                            unit_from_byte(w23[i].z, c));
-                    else g = __ldg(reinterpret_cast<const float4*>(lp + (size_t)i * fpitch));
-                    acc[i] = make_float4(__fmul_rn(__fsub_rn(g.x, u.row[i].x), mk[i].x), __fmul_rn(__fsub_rn(g.y, u.row[i].y), mk[i].y),
-                                         __fmul_rn(__fsub_rn(g.z, u.row[i].z), mk[i].z), __fmul_rn(__fsub_rn(g.w, u.row[i].w), mk[i].w));
-                }
-            }
-        }
-        {
-            const Up4x4 u = up_block(hs + (size_t)(3 + c) * CT_HR * CT_FW, 4 * lane, ja, jb, jc, jd);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i < rows) {
-                    float4 g;
-                    if (L0) g = make_float4(unit_from_byte(w01[i].y, c), unit_from_byte(w01[i].w, c), unit_from_byte(w23[i].y, c),
-                                            unit_from_byte(w23[i].w, c));
-                    else g = __ldg(reinterpret_cast<const float4*>(lp + 3 * fstride + (size_t)i * fpitch));
-                    acc[i].x = __fadd_rn(acc[i].x, __fmul_rn(__fsub_rn(g.x, u.row[i].x), __fsub_rn(1.f, mk[i].x)));
-                    acc[i].y = __fadd_rn(acc[i].y, __fmul_rn(__fsub_rn(g.y, u.row[i].y), __fsub_rn(1.f, mk[i].y)));
-                    acc[i].z = __fadd_rn(acc[i].z, __fmul_rn(__fsub_rn(g.z, u.row[i].z), __fsub_rn(1.f, mk[i].z)));
-                    acc[i].w = __fadd_rn(acc[i].w, __fmul_rn(__fsub_rn(g.w, u.row[i].w), __fsub_rn(1.f, mk[i].w)));
-                }
-            }
-        }
-        {
-            const Up4x4 u = up_block(hs + (size_t)(6 + c) * CT_HR * CT_FW, 4 * lane, ja, jb, jc, jd);
-            float* __restrict__ op = out_fine + ((size_t)f * 3 + c) * ostride + (size_t)fy * opitch + fx;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i < rows)
-                    *reinterpret_cast<float4*>(op + (size_t)i * opitch) =
-                        make_float4(__fadd_rn(u.row[i].x, acc[i].x), __fadd_rn(u.row[i].y, acc[i].y),
-                                    __fadd_rn(u.row[i].z, acc[i].z), __fadd_rn(u.row[i].w, acc[i].w));
-            }
-        }
-    }
-}
-
-// frame's blend mask as a plane (stage dumps only; the render path evaluates it inside the pyramid kernels)
-__global__ void k_mask_plane(const float* __restrict__ basis, int bpitch, const FrameParams* __restrict__ fp, int f,
-                             float* __restrict__ out, int w, int h) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
-    out[(size_t)y * w + x] = blend_mask(basis[(size_t)y * bpitch + x], fp[f].mask_alpha, fp[f].mask_beta);
+__global__ void __launch_bounds__(96)
+k_collapse_roll(const uint2* __restrict__ warped, int wpitch, const float* __restrict__ mask0, int mpitch, size_t m0stride,
+                const float* __restrict__ g_fine, int w, int h, int fpitch, size_t fstride, const float* __restrict__ g_coarse,
+                const float* __restrict__ out_coarse, int cw, int ch, int cpitch, size_t cstride, float* __restrict__ out_fine,
+                int opitch, size_t ostride) {
+    const int f = blockIdx.z, c = threadIdx.y;
+    const int fx = blockIdx.x * 128 + 4 * threadIdx.x, cy0 = blockIdx.y * CL_R;
+    CollapseArgs A;
+    A.wframe = L0 ? warped + (size_t)f * h * wpitch : nullptr; A.wpitch = wpitch;
+    A.mask0 = L0 ? mask0 + (size_t)f * m0stride : nullptr; A.mpitch = mpitch;
+    A.gfine = L0 ? nullptr : g_fine + (size_t)f * 7 * fstride; A.fpitch = fpitch; A.fstride = fstride;
+    A.gc = g_coarse + (size_t)f * 7 * cstride; A.oc = out_coarse + (size_t)f * 3 * cstride;
+    A.cw = cw; A.ch = ch; A.cpitch = cpitch; A.cstride = cstride;
+    A.out = out_fine + (size_t)f * 3 * ostride; A.opitch = opitch; A.ostride = ostride; A.w = w; A.h = h;
+    const int a = fx >> 1;
+    const bool lane_in = a >= 1 && a + 2 <= cw - 1;                       // implies fx + 3 < w
+    const bool rows_in = cy0 >= 1 && cy0 + CL_R <= ch - 1 && 2 * (cy0 + CL_R) <= h;
+    if (__all_sync(FULL, lane_in && rows_in)) collapse_body<L0, true>(A, c, fx, cy0);
+    else if (fx < w) collapse_body<L0, false>(A, c, fx, cy0);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 void launch_pyr_down0(cudaStream_t st, const uint2* warped, int wpitch, const float* basis, int bpitch,
-                      const FrameParams* fp, int w, int h, float* dst, LevelDesc dl, int frames) {
-    static const size_t smem = (size_t)7 * PD_IR * PD_OW * sizeof(float);
-    static bool once = false;
-    if (!once) {
-        cudaFuncSetAttribute(k_pyr_down0_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        once = true;
-    }
-    k_pyr_down0_tile<<<dim3(div_up(dl.w, PD_OW), div_up(dl.h, PD_OH), frames), 256, smem, st>>>(
-        warped, wpitch, basis, bpitch, fp, w, h, dst, dl.w, dl.h, dl.pitch, dl.plane_stride);
+                      const FrameParams* fp, int w, int h, float* mask0, size_t m0stride, float* dst, LevelDesc dl,
+                      int frames) {
+    k_pyr_down0_roll<<<dim3(div_up(dl.w, 128), div_up(dl.h, DN_R), frames), dim3(32, 7), 0, st>>>(
+        warped, wpitch, basis, bpitch, fp, w, h, mask0, m0stride, dst, dl.w, dl.h, dl.pitch, dl.plane_stride);
 }
 
 void launch_pyr_down(cudaStream_t st, const float* src, LevelDesc sl, float* dst, LevelDesc dl, int frames) {
-    k_pyr_down_tile<<<dim3(div_up(dl.w, PD_OW), div_up(dl.h, PD_OH), frames * 7), 256, 0, st>>>(
+    k_pyr_down_roll<<<dim3(div_up(dl.w, 128), div_up(dl.h, 4 * DN_R), frames * 7), dim3(32, 4), 0, st>>>(
         src, sl.w, sl.h, sl.pitch, sl.plane_stride, dst, dl.w, dl.h, dl.pitch, dl.plane_stride);
 }
 
@@ -458,32 +507,17 @@ void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* 
 
 void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
                      LevelDesc cl, float* out_fine, int frames) {
-    static bool once = false;
-    if (!once) {
-        cudaFuncSetAttribute(k_collapse_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM);
-        once = true;
-    }
-    k_collapse_tile<false><<<dim3(div_up(fl.w, CT_FW), div_up(fl.h, CT_FH), frames), 256, CT_SMEM, st>>>(
-        nullptr, 0, nullptr, 0, nullptr, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse, out_coarse, cl.w, cl.h,
-        cl.pitch, cl.plane_stride, out_fine, fl.pitch, fl.plane_stride);
+    k_collapse_roll<false><<<dim3(div_up(fl.w, 128), div_up(fl.h, 2 * CL_R), frames), dim3(32, 3), 0, st>>>(
+        nullptr, 0, nullptr, 0, 0, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
+        cl.plane_stride, out_fine, fl.pitch, fl.plane_stride);
 }
 
-void launch_collapse0(cudaStream_t st, const uint2* warped, int wpitch, const float* basis, int bpitch,
-                      const FrameParams* fp, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
-                      float* out_fine, LevelDesc ol, int frames) {
-    static bool once = false;
-    if (!once) {
-        cudaFuncSetAttribute(k_collapse_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM);
-        once = true;
-    }
-    k_collapse_tile<true><<<dim3(div_up(w, CT_FW), div_up(h, CT_FH), frames), 256, CT_SMEM, st>>>(
-        warped, wpitch, basis, bpitch, fp, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
+void launch_collapse0(cudaStream_t st, const uint2* warped, int wpitch, const float* mask0, int mpitch, size_t m0stride,
+                      int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl, float* out_fine,
+                      LevelDesc ol, int frames) {
+    k_collapse_roll<true><<<dim3(div_up(w, 128), div_up(h, 2 * CL_R), frames), dim3(32, 3), 0, st>>>(
+        warped, wpitch, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
         cl.plane_stride, out_fine, ol.pitch, ol.plane_stride);
-}
-
-void launch_mask_plane(cudaStream_t st, const float* basis, int bpitch, const FrameParams* fp, int frame, float* out, int w,
-                       int h) {
-    k_mask_plane<<<dim3(div_up(w, 256), h), 256, 0, st>>>(basis, bpitch, fp, frame, out, w, h);
 }
 
 }  // namespace poppy

@@ -12,13 +12,15 @@
 //   where ||diff||_2 >= 0.3 (cv::norm of a Vec3f: double accumulation + sqrt): x + amount*diff, else x
 //   (src/util.cpp:135-145, unfused); then cvRound(v*255) saturated to 8 bits (convert_scale.simd.hpp, saturate.hpp:105).
 //
-// Design: one CTA walks a 120-column strip of the frame downwards, 8 rows per step, keeping three small rings in
+// Design: one CTA walks a 120-column strip of the frame downwards, 8 rows per step, keeping three 16-row rings in
 // shared memory (the input rows, their row-pass results, and the blur differences), so the 9x9 + 3x3 footprint costs
-// no vertical halo and every input value is read from global memory once (plus 8/120 horizontally). Per step:
+// no vertical halo and every input value is read from global memory once (plus 8/120 horizontally). The step loop is
+// unrolled by two: rows advance by 8 per step, so with 16-row rings every ring slot is a compile-time constant of the
+// step parity and shared-memory accesses need no address arithmetic. Per step:
 //   R  one warp per (row, channel): load 4 px per lane, exchange the horizontal neighbours through the input ring,
 //      row pass -> row-pass ring
-//   C  column pass with a 12-row register window per thread (4 columns x 4 rows), diff -> diff ring; a per-row bit
-//      mask records which 4-px groups hold any |diff| >= 0.17
+//   C  column pass with a 12-row register window per thread (4 columns x 4 rows), diff -> diff ring; a bit mask per
+//      (row, channel) records which 4-px groups hold any |diff| >= 0.17
 //   M  8 rows x 30 groups: where no flagged group touches the 3x3 window the median cannot reach the 0.3 threshold
 //      (|median| <= max |diff| < 0.3/sqrt(3)), so the pixel is the input; otherwise the exact median/norm/sharpen runs.
 //      Rounding to 8 bits uses the magic-number trick of pixel_ops.cuh; rows are written as three 32-bit words per lane.
@@ -34,11 +36,10 @@ constexpr int US_W = 120;            // output columns per strip
 constexpr int US_CW = 128;           // computed columns x0-4 .. x0+123
 constexpr int US_XW = 136;           // staged input columns x0-8 .. x0+127
 constexpr int US_STEP = 8;           // rows per step
-constexpr int US_RING = 16;          // ring depth of the input and row-pass rings
-constexpr int US_DRING = 12;         // ring depth of the diff ring
+constexpr int US_RING = 16;          // ring depth (rows) of the three shared-memory rings
 constexpr int US_CHUNK = 216;        // rows per CTA
-constexpr size_t US_SMEM = ((size_t)US_RING * 3 * US_XW + (size_t)US_RING * 3 * US_CW + (size_t)US_DRING * 3 * US_CW) * sizeof(float) +
-                           US_DRING * sizeof(uint32_t);
+constexpr size_t US_SMEM = ((size_t)US_RING * 3 * US_XW + 2 * (size_t)US_RING * 3 * US_CW) * sizeof(float) +
+                           US_RING * 4 * sizeof(uint32_t);
 constexpr float US_FLAG_T = 0.17f;   // 3 * 0.17^2 = 0.0867 < 0.09: below this no median can reach the threshold
 
 // getGaussianKernel(9, 1, CV_32F) (bit-exact kernel, OCV imgproc/src/smooth.dispatch.cpp:81-198): centre .. edge
@@ -89,6 +90,200 @@ __device__ __forceinline__ float col9(float w0, float w1, float w2, float w3, fl
     return __fadd_rn(s, __fmul_rn(gk(4), __fadd_rn(w8, w0)));
 }
 
+// Per-thread constants of the strip kernel.
+struct UsThread {
+    int w, h, lane, warp, gx0, x0, Y0, Y1, tail_from;
+    bool in_img;          // the lane's 4 computed columns start inside the image
+    bool lane_fast;       // all 12 row-pass taps inside the image and in the vector-body region
+    bool halo;            // lane 0 / 1 stage the 4 columns left / right of the computed range
+    int halo_goff;        // their offset from column gx0 in global memory ...
+    int halo_soff;        // ... and their float offset in an input-ring row
+};
+
+constexpr int US_XROW = 3 * US_XW, US_CROW = 3 * US_CW;      // floats per ring row (3 channels)
+
+// R: row pass of virtual row vb + 5 + warp, all three channels. SLOT-independent: the ring slot is passed in.
+__device__ __forceinline__ void us_row_pass(const UsThread& T, const float* __restrict__ img, int pitch, size_t stride,
+                                            float* xs_row, float* rp_row, int v) {
+    const float* __restrict__ row = img + (size_t)reflect101(v, T.h) * pitch + T.gx0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c, row += stride) {
+        float* xrow = xs_row + c * US_XW;
+        float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (T.in_img) {
+            own = __ldg(reinterpret_cast<const float4*>(row));
+            *reinterpret_cast<float4*>(xrow + 4 + 4 * T.lane) = own;
+        }
+        if (T.halo) *reinterpret_cast<float4*>(xrow + T.halo_soff) = __ldg(reinterpret_cast<const float4*>(row + T.halo_goff));
+        __syncwarp();
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (T.lane_fast) {
+            const float4 lft = *reinterpret_cast<const float4*>(xrow + 4 * T.lane);
+            const float4 rgt = *reinterpret_cast<const float4*>(xrow + 8 + 4 * T.lane);
+            const float t[12] = {lft.x, lft.y, lft.z, lft.w, own.x, own.y, own.z, own.w, rgt.x, rgt.y, rgt.z, rgt.w};
+            o.x = row9(t + 0, true); o.y = row9(t + 1, true); o.z = row9(t + 2, true); o.w = row9(t + 3, true);
+        } else {
+            float r[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* __restrict__ row0 = row - T.gx0;
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                const int gx = T.gx0 + i;
+                if (gx < 0 || gx >= T.w) continue;
+                if (T.w == 1) { r[i] = __ldg(row0); continue; }      // GaussianBlur shrinks the kernel to [1] on a 1-pixel axis
+                float t[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) t[j] = __ldg(row0 + reflect101(gx - 4 + j, T.w));
+                r[i] = row9(t, 3 * gx + c < T.tail_from);
+            }
+            o = make_float4(r[0], r[1], r[2], r[3]);
+        }
+        *reinterpret_cast<float4*>(rp_row + c * US_CW + 4 * T.lane) = o;
+    }
+}
+
+// C: column pass + diff of rows vb+1+4*HF .. +3 for channel c; every ring slot is a compile-time constant.
+template <int PAR, int HF>
+__device__ __forceinline__ void us_col_pass(const UsThread& T, const float* rp_t, const float* xs_t, float* df_t,
+                                            uint32_t* fl_c, int vb, int c) {
+    constexpr int K0 = 8 * PAR + 4 * HF - 3;                 // window row j lives in ring slot (K0 + j) & 15
+    const int v0 = vb + 1 + 4 * HF;
+    const int lo = max(T.Y0 - 1, 0), hi = min(T.Y1, T.h - 1);          // diff rows this CTA needs: [lo, hi]
+    if (v0 + 3 < lo || v0 > hi) return;
+    float4 win[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) win[j] = *reinterpret_cast<const float4*>(rp_t + ((K0 + j) & 15) * US_CROW);
+    const bool fused = 3 * (T.gx0 + 3) + c < T.tail_from;         // whole group in the vector body
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        constexpr int dummy = 0; (void)dummy;
+        const int slot = (K0 + 4 + i) & 15;
+        const int v = v0 + i;
+        if (v < lo || v > hi) continue;                            // warp-uniform
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool big = false;
+        if (T.in_img) {
+            float4 b;
+            if (T.h == 1) {
+                b = win[4 + i];
+            } else if (fused) {
+                b.x = col9(win[i].x, win[i + 1].x, win[i + 2].x, win[i + 3].x, win[i + 4].x, win[i + 5].x, win[i + 6].x, win[i + 7].x, win[i + 8].x, true);
+                b.y = col9(win[i].y, win[i + 1].y, win[i + 2].y, win[i + 3].y, win[i + 4].y, win[i + 5].y, win[i + 6].y, win[i + 7].y, win[i + 8].y, true);
+                b.z = col9(win[i].z, win[i + 1].z, win[i + 2].z, win[i + 3].z, win[i + 4].z, win[i + 5].z, win[i + 6].z, win[i + 7].z, win[i + 8].z, true);
+                b.w = col9(win[i].w, win[i + 1].w, win[i + 2].w, win[i + 3].w, win[i + 4].w, win[i + 5].w, win[i + 6].w, win[i + 7].w, win[i + 8].w, true);
+            } else {
+                b.x = col9(win[i].x, win[i + 1].x, win[i + 2].x, win[i + 3].x, win[i + 4].x, win[i + 5].x, win[i + 6].x, win[i + 7].x, win[i + 8].x, 3 * (T.gx0 + 0) + c < T.tail_from);
+                b.y = col9(win[i].y, win[i + 1].y, win[i + 2].y, win[i + 3].y, win[i + 4].y, win[i + 5].y, win[i + 6].y, win[i + 7].y, win[i + 8].y, 3 * (T.gx0 + 1) + c < T.tail_from);
+                b.z = col9(win[i].z, win[i + 1].z, win[i + 2].z, win[i + 3].z, win[i + 4].z, win[i + 5].z, win[i + 6].z, win[i + 7].z, win[i + 8].z, 3 * (T.gx0 + 2) + c < T.tail_from);
+                b.w = col9(win[i].w, win[i + 1].w, win[i + 2].w, win[i + 3].w, win[i + 4].w, win[i + 5].w, win[i + 6].w, win[i + 7].w, win[i + 8].w, 3 * (T.gx0 + 3) + c < T.tail_from);
+            }
+            const float4 x = *reinterpret_cast<const float4*>(xs_t + slot * US_XROW);
+            d = make_float4(__fsub_rn(x.x, b.x), __fsub_rn(x.y, b.y), __fsub_rn(x.z, b.z), __fsub_rn(x.w, b.w));
+            // columns past the image hold padding: keep them out of the flags
+            const float m0 = fabsf(d.x), m1 = T.gx0 + 1 < T.w ? fabsf(d.y) : 0.f, m2 = T.gx0 + 2 < T.w ? fabsf(d.z) : 0.f,
+                        m3 = T.gx0 + 3 < T.w ? fabsf(d.w) : 0.f;
+            big = !(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) < US_FLAG_T);
+        }
+        *reinterpret_cast<float4*>(df_t + slot * US_CROW) = d;
+        const uint32_t bits = __ballot_sync(0xffffffffu, big);
+        if (T.lane == 0) fl_c[slot * 4] = bits;
+    }
+}
+
+// M: median / threshold / sharpen / 8-bit store of row vb + warp.
+template <int PAR>
+__device__ __forceinline__ void us_emit(const UsThread& T, const float* xs, const float* df, const uint32_t* fl, int vb,
+                                        float amount, double norm_thr2, uint8_t* __restrict__ dst, bool dst_words) {
+    const int y = vb + T.warp, gx = T.x0 + 4 * T.lane;
+    if (y >= T.Y1 || T.lane >= US_W / 4 || gx >= T.w) return;
+    const int ym = max(y - 1, 0), yp = min(y + 1, T.h - 1);
+    const int sc = (8 * PAR + T.warp) & 15, sm = (sc + (ym - y)) & 15, sp = (sc + (yp - y)) & 15;
+    // computed-column group of gx is lane+1; its 3x3 windows reach groups lane .. lane+2
+    const uint4 fa = *reinterpret_cast<const uint4*>(fl + sm * 4), fb = *reinterpret_cast<const uint4*>(fl + sc * 4),
+                fc = *reinterpret_cast<const uint4*>(fl + sp * 4);
+    const uint32_t flagged = (fa.x | fa.y | fa.z | fb.x | fb.y | fb.z | fc.x | fc.y | fc.z) & (7u << T.lane);
+    const float* xrow = xs + sc * US_XROW + 8 + 4 * T.lane;
+    float4 px[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) px[c] = *reinterpret_cast<const float4*>(xrow + c * US_XW);
+    float v[3][4] = {{px[0].x, px[0].y, px[0].z, px[0].w}, {px[1].x, px[1].y, px[1].z, px[1].w}, {px[2].x, px[2].y, px[2].z, px[2].w}};
+    const int npx = min(4, T.w - gx);
+    if (flagged) {
+#pragma unroll 1
+        for (int i = 0; i < npx; ++i) {
+            const int cc = 4 + 4 * T.lane + i;                            // column in the diff ring
+            const int cm = max(gx + i - 1, 0) - (T.x0 - 4), cp = min(gx + i + 1, T.w - 1) - (T.x0 - 4);
+            float med[3];
+            double nn = 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* d0 = df + sm * US_CROW + c * US_CW;
+                const float* d1 = df + sc * US_CROW + c * US_CW;
+                const float* d2 = df + sp * US_CROW + c * US_CW;
+                med[c] = median9(d0[cm], d0[cc], d0[cp], d1[cm], d1[cc], d1[cp], d2[cm], d2[cc], d2[cp]);
+                nn = __dadd_rn(nn, __dmul_rn((double)med[c], (double)med[c]));
+            }
+            if (nn >= norm_thr2) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float add = __fmul_rn(amount, med[c]);
+                    // static indexing keeps v[][] in registers
+                    if (i == 0) v[c][0] = __fadd_rn(v[c][0], add);
+                    else if (i == 1) v[c][1] = __fadd_rn(v[c][1], add);
+                    else if (i == 2) v[c][2] = __fadd_rn(v[c][2], add);
+                    else v[c][3] = __fadd_rn(v[c][3], add);
+                }
+            }
+        }
+    }
+    float q[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[c][i] = u8_magic(v[c][i]);
+    uint8_t* drow = dst + ((size_t)y * T.w + gx) * 3;
+    if (dst_words && npx == 4) {
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(drow);
+        d32[0] = pack_u8x4(q[0][0], q[1][0], q[2][0], q[0][1]);
+        d32[1] = pack_u8x4(q[1][1], q[2][1], q[0][2], q[1][2]);
+        d32[2] = pack_u8x4(q[2][2], q[0][3], q[1][3], q[2][3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < npx) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) drow[3 * i + c] = (uint8_t)(__float_as_uint(q[c][i]) & 255u);
+            }
+    }
+}
+
+// One step (8 rows) of the strip walk; PAR = step parity, which fixes every ring slot at compile time
+// (rows advance by 8 per step, the rings hold 16 rows).
+template <int PAR>
+__device__ __forceinline__ void us_step(const UsThread& T, int s, const float* __restrict__ img, int pitch, size_t stride,
+                                        float* xs, float* rp, float* df, uint32_t* fl, float amount, double norm_thr2,
+                                        uint8_t* __restrict__ dst, bool dst_words) {
+    const int vb = T.Y0 + US_STEP * s;
+    {   // R: virtual row vb + 5 + warp
+        const int v = vb + 5 + T.warp;
+        if (v >= T.Y0 - 5 && v <= T.Y1 + 4) {
+            const int slot = (8 * PAR + 5 + T.warp) & 15;
+            us_row_pass(T, img, pitch, stride, xs + slot * US_XROW, rp + slot * US_CROW, v);
+        }
+    }
+    __syncthreads();
+    if (T.warp < 6) {
+        const int c = T.warp >> 1;
+        const float* rp_t = rp + c * US_CW + 4 * T.lane;
+        const float* xs_t = xs + c * US_XW + 4 + 4 * T.lane;
+        float* df_t = df + c * US_CW + 4 * T.lane;
+        if (T.warp & 1) us_col_pass<PAR, 1>(T, rp_t, xs_t, df_t, fl + c, vb, c);
+        else us_col_pass<PAR, 0>(T, rp_t, xs_t, df_t, fl + c, vb, c);
+    }
+    __syncthreads();
+    if (s >= 0) us_emit<PAR>(T, xs, df, fl, vb, amount, norm_thr2, dst, dst_words);
+    __syncthreads();
+}
+
 }  // namespace
 
 // block 256; grid (ceil(w/120), ceil(h/216), frames); dynamic shared memory US_SMEM.
@@ -97,182 +292,33 @@ __global__ void __launch_bounds__(256, 3)
 k_unsharp_strip(const float* __restrict__ lap, int w, int h, int pitch, size_t stride, const FrameParams* __restrict__ fp,
                 double norm_thr2, uint8_t* __restrict__ frames_base, size_t frame_bytes) {
     extern __shared__ __align__(16) float smem_dyn[];
-    float* xs = smem_dyn;                                        // [US_RING][3][US_XW]   input rows (virtual, reflected)
-    float* rp = xs + US_RING * 3 * US_XW;                        // [US_RING][3][US_CW]   row-pass results
-    float* df = rp + US_RING * 3 * US_CW;                        // [US_DRING][3][US_CW]  x - blur
-    uint32_t* fl = reinterpret_cast<uint32_t*>(df + US_DRING * 3 * US_CW);   // [US_DRING] flagged 4-px groups per diff row
+    float* xs = smem_dyn;                                        // [US_RING][3][US_XW]  input rows (virtual, reflected)
+    float* rp = xs + US_RING * US_XROW;                          // [US_RING][3][US_CW]  row-pass results
+    float* df = rp + US_RING * US_CROW;                          // [US_RING][3][US_CW]  x - blur
+    uint32_t* fl = reinterpret_cast<uint32_t*>(df + US_RING * US_CROW);      // [US_RING][4] flagged 4-px groups per diff row, channel
 
     const int f = blockIdx.z;
-    const int x0 = blockIdx.x * US_W, Y0 = blockIdx.y * US_CHUNK, Y1 = min(Y0 + US_CHUNK, h);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    UsThread T;
+    T.w = w; T.h = h;
+    T.x0 = blockIdx.x * US_W; T.Y0 = blockIdx.y * US_CHUNK; T.Y1 = min(T.Y0 + US_CHUNK, h);
+    T.warp = threadIdx.x >> 5; T.lane = threadIdx.x & 31;
+    T.tail_from = 3 * w - (3 * w) % 8;       // first interleaved element handled by the scalar filter loops
+    T.gx0 = T.x0 - 4 + 4 * T.lane;           // this lane's 4 computed columns
+    T.in_img = T.gx0 >= 0 && T.gx0 < w;
+    // all 12 taps of the lane's 4 pixels inside the image, none of them in the scalar-tail region
+    T.lane_fast = T.gx0 - 4 >= 0 && T.gx0 + 7 <= w - 1 && 3 * (T.gx0 + 3) + 2 < T.tail_from && w > 1;
+    T.halo = (T.lane == 0 && T.x0 - 8 >= 0) || (T.lane == 1 && T.x0 + 124 < w);
+    T.halo_goff = T.lane == 0 ? -4 : 124;    // lane 0: columns x0-8.. (gx0 = x0-4); lane 1: columns x0+124.. (gx0 = x0)
+    T.halo_soff = T.lane == 0 ? 0 : US_XW - 4;
     const float* __restrict__ img = lap + (size_t)f * 3 * stride;
-    const int tail_from = 3 * w - (3 * w) % 8;       // first interleaved element handled by the scalar filter loops
     const FrameParams P = fp[f];
     uint8_t* __restrict__ dst = frames_base + (size_t)P.dst_slot * frame_bytes;
-    const size_t dst_pitch = (size_t)w * 3;
     const bool dst_words = (w & 3) == 0 && ((size_t)dst & 3) == 0;
+    const int n_steps = div_up(T.Y1 - T.Y0, US_STEP);
 
-    // ring slots: virtual row v >= Y0 - 16 always
-    auto slot16 = [&](int v) { return (v - Y0 + 32) & (US_RING - 1); };
-    auto slot12 = [&](int v) { return (v - Y0 + 24) % US_DRING; };
-
-    const int gx0 = x0 - 4 + 4 * lane;               // this lane's 4 computed columns
-    // all 12 taps of the lane's 4 pixels inside the image, none of them in the scalar-tail region
-    const bool lane_fast = gx0 - 4 >= 0 && gx0 + 7 <= w - 1 && 3 * (gx0 + 3) + 2 < tail_from && w > 1;
-    const int n_steps = div_up(Y1 - Y0, US_STEP);
-
-    for (int s = -2; s < n_steps; ++s) {
-        const int vb = Y0 + US_STEP * s;             // step base row
-        // ---------------- R: row pass of virtual rows vb+5 .. vb+12 (those >= Y0-5) --------------------------------
-        for (int task = warp; task < US_STEP * 3; task += 8) {
-            const int v = vb + 5 + task / 3, c = task % 3;
-            if (v < Y0 - 5 || v > Y1 + 4) continue;
-            const float* __restrict__ row = img + (size_t)c * stride + (size_t)reflect101(v, h) * pitch;
-            float* xrow = xs + ((size_t)slot16(v) * 3 + c) * US_XW;
-            float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gx0 >= 0 && gx0 < w) {
-                own = __ldg(reinterpret_cast<const float4*>(row + gx0));
-                *reinterpret_cast<float4*>(xrow + 4 + 4 * lane) = own;
-            }
-            if (lane == 0 && x0 - 8 >= 0) *reinterpret_cast<float4*>(xrow) = __ldg(reinterpret_cast<const float4*>(row + x0 - 8));
-            if (lane == 1 && x0 + 124 < w)
-                *reinterpret_cast<float4*>(xrow + US_XW - 4) = __ldg(reinterpret_cast<const float4*>(row + x0 + 124));
-            __syncwarp();
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane_fast) {
-                const float4 lft = *reinterpret_cast<const float4*>(xrow + 4 * lane);
-                const float4 rgt = *reinterpret_cast<const float4*>(xrow + 8 + 4 * lane);
-                const float t[12] = {lft.x, lft.y, lft.z, lft.w, own.x, own.y, own.z, own.w, rgt.x, rgt.y, rgt.z, rgt.w};
-                o.x = row9(t + 0, true); o.y = row9(t + 1, true); o.z = row9(t + 2, true); o.w = row9(t + 3, true);
-            } else {
-                float r[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-                for (int i = 0; i < 4; ++i) {
-                    const int gx = gx0 + i;
-                    if (gx < 0 || gx >= w) continue;
-                    if (w == 1) { r[i] = __ldg(row); continue; }      // GaussianBlur shrinks the kernel to [1] on a 1-pixel axis
-                    float t[9];
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) t[j] = __ldg(row + reflect101(gx - 4 + j, w));
-                    r[i] = row9(t, 3 * gx + c < tail_from);
-                }
-                o = make_float4(r[0], r[1], r[2], r[3]);
-            }
-            *reinterpret_cast<float4*>(rp + ((size_t)slot16(v) * 3 + c) * US_CW + 4 * lane) = o;
-        }
-        if (tid < US_STEP) fl[slot12(vb + 1 + tid)] = 0u;
-        __syncthreads();
-
-        // ---------------- C: column pass + diff of rows vb+1 .. vb+8 -----------------------------------------------
-        if (warp < 6) {
-            const int c = warp >> 1, v0 = vb + 1 + 4 * (warp & 1);
-            const int lo = max(Y0 - 1, 0), hi = min(Y1, h - 1);          // diff rows needed by this CTA: [lo, hi]
-            if (v0 + 3 >= lo && v0 <= hi) {
-                float4 win[12];
-#pragma unroll
-                for (int j = 0; j < 12; ++j)
-                    win[j] = *reinterpret_cast<const float4*>(rp + ((size_t)slot16(v0 - 4 + j) * 3 + c) * US_CW + 4 * lane);
-                const bool fused = 3 * (gx0 + 3) + c < tail_from;         // whole group in the vector body
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int v = v0 + i;
-                    const bool need = v >= lo && v <= hi;                  // warp-uniform
-                    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-                    bool big = false;
-                    if (need && gx0 >= 0 && gx0 < w) {
-                        float4 b;
-                        if (h == 1) {
-                            b = win[4 + i];
-                        } else if (fused) {
-                            b.x = col9(win[i].x, win[i + 1].x, win[i + 2].x, win[i + 3].x, win[i + 4].x, win[i + 5].x, win[i + 6].x, win[i + 7].x, win[i + 8].x, true);
-                            b.y = col9(win[i].y, win[i + 1].y, win[i + 2].y, win[i + 3].y, win[i + 4].y, win[i + 5].y, win[i + 6].y, win[i + 7].y, win[i + 8].y, true);
-                            b.z = col9(win[i].z, win[i + 1].z, win[i + 2].z, win[i + 3].z, win[i + 4].z, win[i + 5].z, win[i + 6].z, win[i + 7].z, win[i + 8].z, true);
-                            b.w = col9(win[i].w, win[i + 1].w, win[i + 2].w, win[i + 3].w, win[i + 4].w, win[i + 5].w, win[i + 6].w, win[i + 7].w, win[i + 8].w, true);
-                        } else {
-                            b.x = col9(win[i].x, win[i + 1].x, win[i + 2].x, win[i + 3].x, win[i + 4].x, win[i + 5].x, win[i + 6].x, win[i + 7].x, win[i + 8].x, 3 * (gx0 + 0) + c < tail_from);
-                            b.y = col9(win[i].y, win[i + 1].y, win[i + 2].y, win[i + 3].y, win[i + 4].y, win[i + 5].y, win[i + 6].y, win[i + 7].y, win[i + 8].y, 3 * (gx0 + 1) + c < tail_from);
-                            b.z = col9(win[i].z, win[i + 1].z, win[i + 2].z, win[i + 3].z, win[i + 4].z, win[i + 5].z, win[i + 6].z, win[i + 7].z, win[i + 8].z, 3 * (gx0 + 2) + c < tail_from);
-                            b.w = col9(win[i].w, win[i + 1].w, win[i + 2].w, win[i + 3].w, win[i + 4].w, win[i + 5].w, win[i + 6].w, win[i + 7].w, win[i + 8].w, 3 * (gx0 + 3) + c < tail_from);
-                        }
-                        const float4 x = *reinterpret_cast<const float4*>(xs + ((size_t)slot16(v) * 3 + c) * US_XW + 4 + 4 * lane);
-                        d = make_float4(__fsub_rn(x.x, b.x), __fsub_rn(x.y, b.y), __fsub_rn(x.z, b.z), __fsub_rn(x.w, b.w));
-                        // columns past the image hold padding: keep them out of the flags
-                        const float m0 = fabsf(d.x), m1 = gx0 + 1 < w ? fabsf(d.y) : 0.f, m2 = gx0 + 2 < w ? fabsf(d.z) : 0.f,
-                                    m3 = gx0 + 3 < w ? fabsf(d.w) : 0.f;
-                        big = !(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) < US_FLAG_T);
-                    }
-                    if (need) {
-                        *reinterpret_cast<float4*>(df + ((size_t)slot12(v) * 3 + c) * US_CW + 4 * lane) = d;
-                        const uint32_t bits = __ballot_sync(0xffffffffu, big);
-                        if (lane == 0 && bits) atomicOr(&fl[slot12(v)], bits);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---------------- M: median / threshold / sharpen / 8-bit store of rows vb .. vb+7 --------------------------
-        const int y = vb + warp, gx = x0 + 4 * lane;
-        if (s >= 0 && y < Y1 && lane < US_W / 4 && gx < w) {
-            const int ym = max(y - 1, 0), yp = min(y + 1, h - 1);
-            const int sm = slot12(ym), sc = slot12(y), sp = slot12(yp);
-            // computed-column group of gx is lane+1; its 3x3 windows reach groups lane .. lane+2
-            const uint32_t flagged = (fl[sm] | fl[sc] | fl[sp]) & (7u << lane);
-            const float* xrow = xs + (size_t)slot16(y) * 3 * US_XW + 8 + 4 * lane;
-            float4 px[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) px[c] = *reinterpret_cast<const float4*>(xrow + c * US_XW);
-            float v[3][4] = {{px[0].x, px[0].y, px[0].z, px[0].w}, {px[1].x, px[1].y, px[1].z, px[1].w}, {px[2].x, px[2].y, px[2].z, px[2].w}};
-            const int npx = min(4, w - gx);
-            if (flagged) {
-#pragma unroll 1
-                for (int i = 0; i < npx; ++i) {
-                    const int cc = 4 + 4 * lane + i;                            // column in the diff ring
-                    const int cm = max(gx + i - 1, 0) - (x0 - 4), cp = min(gx + i + 1, w - 1) - (x0 - 4);
-                    float med[3];
-                    double nn = 0.0;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float* d0 = df + ((size_t)sm * 3 + c) * US_CW;
-                        const float* d1 = df + ((size_t)sc * 3 + c) * US_CW;
-                        const float* d2 = df + ((size_t)sp * 3 + c) * US_CW;
-                        med[c] = median9(d0[cm], d0[cc], d0[cp], d1[cm], d1[cc], d1[cp], d2[cm], d2[cc], d2[cp]);
-                        nn = __dadd_rn(nn, __dmul_rn((double)med[c], (double)med[c]));
-                    }
-                    if (nn >= norm_thr2) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float add = __fmul_rn(P.amount, med[c]);
-                            // static indexing keeps v[][] in registers
-                            if (i == 0) v[c][0] = __fadd_rn(v[c][0], add);
-                            else if (i == 1) v[c][1] = __fadd_rn(v[c][1], add);
-                            else if (i == 2) v[c][2] = __fadd_rn(v[c][2], add);
-                            else v[c][3] = __fadd_rn(v[c][3], add);
-                        }
-                    }
-                }
-            }
-            float q[3][4];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) q[c][i] = u8_magic(v[c][i]);
-            uint8_t* drow = dst + (size_t)y * dst_pitch + (size_t)gx * 3;
-            if (dst_words && npx == 4) {
-                uint32_t* d32 = reinterpret_cast<uint32_t*>(drow);
-                d32[0] = pack_u8x4(q[0][0], q[1][0], q[2][0], q[0][1]);
-                d32[1] = pack_u8x4(q[1][1], q[2][1], q[0][2], q[1][2]);
-                d32[2] = pack_u8x4(q[2][2], q[0][3], q[1][3], q[2][3]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (i < npx) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) drow[3 * i + c] = (uint8_t)(__float_as_uint(q[c][i]) & 255u);
-                    }
-            }
-        }
-        __syncthreads();
+    for (int s = -2; s < n_steps; s += 2) {
+        us_step<0>(T, s, img, pitch, stride, xs, rp, df, fl, P.amount, norm_thr2, dst, dst_words);
+        if (s + 1 < n_steps) us_step<1>(T, s + 1, img, pitch, stride, xs, rp, df, fl, P.amount, norm_thr2, dst, dst_words);
     }
 }
 

@@ -7,7 +7,7 @@
 //   morphed points    : max_batch_frames x max_points float2
 //   chunk scratch (xB): FrameParams; triangle indices; TriInverse / TriRaster records; triangle-ID map int32 [H][W];
 //                       warped pair uint2 [H][pitch0]; Gaussian levels 1..L (7 planes); collapsed levels 0..L
-//                       (3 planes); the level-0 mask plane exists only for stage dumps
+//                       (3 planes); level-0 blend mask float [H][pitch0]
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -27,8 +27,8 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum KernelClass { KC_POINTS = 0, KC_GEOMETRY, KC_RASTER, KC_WARP, KC_PYR_DOWN, KC_COLLAPSE, KC_UNSHARP, KC_MISC, KC_COUNT };
-const char* const kClassNames[KC_COUNT] = {"lerp_points", "tri_geometry", "raster_triangles", "warp_sample",
+enum KernelClass { KC_POINTS = 0, KC_GEOMETRY, KC_BIN, KC_WARP, KC_PYR_DOWN, KC_COLLAPSE, KC_UNSHARP, KC_MISC, KC_COUNT };
+const char* const kClassNames[KC_COUNT] = {"lerp_points", "tri_geometry", "bin_triangles", "raster_warp",
                                            "pyr_down", "blend_collapse", "unsharp_store", "misc"};
 
 struct TimedLaunch { int cls; cudaEvent_t a, b; };
@@ -62,7 +62,9 @@ struct poppy_cuda_ctx {
     int3* d_tri = nullptr;
     TriInverse* d_inv = nullptr;
     TriRaster* d_rast = nullptr;
-    int* d_trimap = nullptr;
+    int* d_trimap = nullptr;             // stage dumps only (keep_stages)
+    int *d_tile_cnt = nullptr, *d_tile_off = nullptr, *d_tile_list = nullptr, *d_overflow = nullptr;
+    int n_tiles = 0, list_cap = 0;
     uint2* d_warped = nullptr;
     float *d_mask0 = nullptr, *d_g = nullptr, *d_o = nullptr;
     // pinned staging, double buffered
@@ -103,6 +105,8 @@ template <class T> cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc(
 
 void free_chunk(poppy_cuda_ctx* c) {
     cudaFree(c->d_fp); cudaFree(c->d_tri); cudaFree(c->d_inv); cudaFree(c->d_rast); cudaFree(c->d_trimap);
+    cudaFree(c->d_tile_cnt); cudaFree(c->d_tile_off); cudaFree(c->d_tile_list); cudaFree(c->d_overflow);
+    c->d_tile_cnt = nullptr; c->d_tile_off = nullptr; c->d_tile_list = nullptr; c->d_overflow = nullptr;
     cudaFree(c->d_warped); cudaFree(c->d_mask0); cudaFree(c->d_g); cudaFree(c->d_o);
     for (int i = 0; i < 2; ++i) { cudaFreeHost(c->h_fp[i]); cudaFreeHost(c->h_tri[i]); c->h_fp[i] = nullptr; c->h_tri[i] = nullptr; }
     c->d_fp = nullptr; c->d_tri = nullptr; c->d_inv = nullptr; c->d_rast = nullptr; c->d_trimap = nullptr;
@@ -111,7 +115,7 @@ void free_chunk(poppy_cuda_ctx* c) {
 }
 
 size_t per_frame_scratch_bytes(const poppy_cuda_ctx* c) {
-    return c->pixels() * 4 + c->padded_pixels() * 8 + (c->g_floats + c->o_floats) * 4 +
+    return c->padded_pixels() * 12 + (c->g_floats + c->o_floats) * 4 + (size_t)c->list_cap * 4 + (size_t)c->n_tiles * 8 +
            (size_t)c->max_tri * (sizeof(int3) + sizeof(TriInverse) + sizeof(TriRaster));
 }
 
@@ -131,9 +135,13 @@ int ensure_chunk(poppy_cuda_ctx* c) {
     CU_TRY(c, dmalloc(&c->d_tri, B * c->max_tri));
     CU_TRY(c, dmalloc(&c->d_inv, B * c->max_tri));
     CU_TRY(c, dmalloc(&c->d_rast, B * c->max_tri));
-    CU_TRY(c, dmalloc(&c->d_trimap, B * c->pixels()));
+    CU_TRY(c, dmalloc(&c->d_trimap, c->keep_stages ? c->pixels() : 1));
+    CU_TRY(c, dmalloc(&c->d_tile_cnt, B * c->n_tiles));
+    CU_TRY(c, dmalloc(&c->d_tile_off, B * (c->n_tiles + 1)));
+    CU_TRY(c, dmalloc(&c->d_tile_list, B * c->list_cap));
+    CU_TRY(c, dmalloc(&c->d_overflow, B));
     CU_TRY(c, dmalloc(&c->d_warped, B * c->padded_pixels()));
-    CU_TRY(c, dmalloc(&c->d_mask0, c->keep_stages ? c->pixels() : 1));
+    CU_TRY(c, dmalloc(&c->d_mask0, B * c->padded_pixels()));
     CU_TRY(c, dmalloc(&c->d_g, B * c->g_floats));
     CU_TRY(c, dmalloc(&c->d_o, B * c->o_floats));
     for (int i = 0; i < 2; ++i) {
@@ -218,19 +226,24 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
     {   Scope s(c, KC_POINTS);
         launch_lerp_points(st, p1, 0, c->d_pts2, c->d_fp, morphed, c->max_points, n, nb, w, h);
     }
+    CU_TRY(c, cudaMemsetAsync(c->d_tile_cnt, 0, (size_t)nb * c->n_tiles * sizeof(int), st));
     {   Scope s(c, KC_GEOMETRY);
-        launch_tri_geometry(st, c->d_tri, c->d_fp, p1, 0, c->d_pts2, morphed, c->max_points, c->max_tri, tri_max, nb, h,
-                            c->d_inv, c->d_rast);
+        launch_tri_geometry(st, c->d_tri, c->d_fp, p1, 0, c->d_pts2, morphed, c->max_points, c->max_tri, tri_max, nb, w, h,
+                            c->d_inv, c->d_rast, c->d_tile_cnt);
     }
-    CU_TRY(c, cudaMemsetAsync(c->d_trimap, 0, (size_t)nb * c->pixels() * sizeof(int), st));
-    {   Scope s(c, KC_RASTER);
-        launch_raster_triangles(st, c->d_rast, c->d_fp, c->max_tri, tri_max, nb, c->d_trimap, w, h);
+    {   Scope s(c, KC_BIN);
+        c->launches++;          // scan + fill
+        launch_bin_triangles(st, c->d_rast, c->d_fp, c->max_tri, tri_max, nb, w, h, c->d_tile_cnt, c->d_tile_off,
+                             c->d_overflow, c->d_tile_list, c->list_cap);
     }
     {   Scope s(c, KC_WARP);
-        launch_warp(st, c->d_trimap, c->d_inv, c->max_tri, src1, c->d_src2, c->d_warped, c->pitch0(), w, h, nb);
+        launch_raster_warp(st, c->d_rast, c->d_inv, c->d_fp, c->max_tri, c->d_tile_off, c->d_tile_list, c->list_cap,
+                           c->d_overflow, src1, c->d_src2, c->d_warped, c->pitch0(), c->keep_stages ? c->d_trimap : nullptr,
+                           w, h, nb);
     }
     {   Scope s(c, KC_PYR_DOWN);
-        launch_pyr_down0(st, c->d_warped, c->pitch0(), c->d_mbasis, c->pitch0(), c->d_fp, w, h, g_level(c, 1), c->lv[1], nb);
+        launch_pyr_down0(st, c->d_warped, c->pitch0(), c->d_mbasis, c->pitch0(), c->d_fp, w, h, c->d_mask0,
+                         c->padded_pixels(), g_level(c, 1), c->lv[1], nb);
     }
     for (int k = 1; k < L; ++k) {
         Scope s(c, KC_PYR_DOWN);
@@ -244,7 +257,7 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
         launch_collapse(st, g_level(c, k), c->lv[k], g_level(c, k + 1), o_level(c, k + 1), c->lv[k + 1], o_level(c, k), nb);
     }
     {   Scope s(c, KC_COLLAPSE);
-        launch_collapse0(st, c->d_warped, c->pitch0(), c->d_mbasis, c->pitch0(), c->d_fp, w, h, g_level(c, 1),
+        launch_collapse0(st, c->d_warped, c->pitch0(), c->d_mask0, c->pitch0(), c->padded_pixels(), w, h, g_level(c, 1),
                          o_level(c, 1), c->lv[1], o_level(c, 0), c->lv[0], nb);
     }
     {   Scope s(c, KC_UNSHARP);
@@ -309,6 +322,15 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
         c->o_floats += 3 * d.plane_stride;
         lw = (lw + 1) / 2; lh = (lh + 1) / 2;
     }
+    // triangle binning: 64x32 screen tiles; list capacity per frame (a frame that needs more falls back to testing
+    // every triangle in every tile, see k_raster_warp)
+    {
+        const long long tiles = (long long)((width + RW_TW - 1) / RW_TW) * ((height + RW_TH - 1) / RW_TH);
+        c->n_tiles = (int)tiles;
+        const long long all = tiles * max_triangles;
+        const long long want = std::max<long long>(8LL * max_triangles + 4 * tiles, 1LL << 20);
+        c->list_cap = (int)std::min<long long>(all, want);
+    }
     const size_t px = c->pixels();
     CR_TRY(dmalloc(&c->d_src1, px));
     CR_TRY(dmalloc(&c->d_src2, px));
@@ -365,6 +387,16 @@ int poppy_cuda_set_chunk_frames(poppy_cuda_ctx* c, int frames) {
     if (!c) return POPPY_CUDA_ERR_INVALID;
     if (frames < 1) return fail(c, POPPY_CUDA_ERR_INVALID, "chunk frames must be >= 1");
     c->want_chunk = frames;
+    return 0;
+}
+
+int poppy_cuda_set_tile_list_capacity(poppy_cuda_ctx* c, int entries) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (entries < 1) return fail(c, POPPY_CUDA_ERR_INVALID, "tile list capacity must be >= 1");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->list_cap = entries;
+    free_chunk(c);            // reallocated with the new capacity by the next render
     return 0;
 }
 
@@ -584,10 +616,7 @@ int poppy_cuda_debug_read(poppy_cuda_ctx* c, int stage, int frame, void* dst, si
     }
     case POPPY_STAGE_MASK:
         if (int rc = need(px * 4)) return rc;
-        launch_mask_plane(c->stream, c->d_mbasis, c->pitch0(), c->d_fp, 0, c->d_mask0, w, h);
-        CU_TRY(c, cudaGetLastError());
-        CU_TRY(c, cudaStreamSynchronize(c->stream));
-        CU_TRY(c, cudaMemcpy(dst, c->d_mask0, bytes, cudaMemcpyDeviceToHost));
+        CU_TRY(c, cudaMemcpy2D(dst, (size_t)w * 4, c->d_mask0, (size_t)c->pitch0() * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost));
         return 0;
     case POPPY_STAGE_LAP_BLEND: {
         if (int rc = need(px * 12)) return rc;

@@ -42,6 +42,9 @@ class MorphRenderer:
         if stage_timing:
             self._check(self._lib.poppy_cuda_set_stage_timing(self._ctx, 1))
 
+    def set_tile_list_capacity(self, entries_per_frame: int):
+        self._check(self._lib.poppy_cuda_set_tile_list_capacity(self._ctx, int(entries_per_frame)))
+
     # -- plumbing ------------------------------------------------------------------------------------------------
     def _check(self, rc):
         if rc < 0:

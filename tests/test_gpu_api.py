@@ -108,6 +108,26 @@ def test_batched_phases_match_reference_for_any_chunking(chunk):
             assert bits_differ(r.morphed_points(k), pts) == 0
 
 
+def test_tile_list_overflow_path_is_exact():
+    """A frame whose binned triangle lists do not fit the list capacity is rasterised by testing every triangle in
+    every tile; the frames must not change."""
+    ref = _ref()
+    from poppy_b200.renderer import MorphRenderer
+    w, h, levels = 400, 300, 5
+    inp = synth.make_inputs(w, h, 300, 8.0, seed=21)
+    phases = np.array([0.2, 0.8], np.float32)
+    plan = host.SequencePlan(inp.pts1, inp.pts2, w, h, phases)
+    with MorphRenderer(w, h, levels, len(inp.pts1), plan.max_triangles, len(phases)) as r:
+        r.set_tile_list_capacity(7)            # far fewer than the ~600 triangles of a frame
+        r.set_pair(inp.bgr1, inp.bgr2, inp.gabor2)
+        r.set_points(inp.pts1, inp.pts2)
+        r.render(phases, phases.astype(np.float64), plan.tri_idx, plan.tri_offsets)
+        frames = r.download(0, len(phases))
+        for k, s in enumerate(phases):
+            want, _ = ref.morph_images(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, float(s), float(s), levels)
+            assert bits_differ(frames[k], want) == 0, k
+
+
 FRAME_FILES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
                      if not os.path.basename(f).startswith(("chain_", "topology")))
 

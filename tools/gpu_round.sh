@@ -12,7 +12,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
    python bench.py --frames 16 --steps 1 --warmup 3 --cpu-frames 0 --e2e-steps 0 --no-stage-pass > gpurun_out/ncu_list_${TAG}.log 2>&1
 tail -3 gpurun_out/ncu_list_${TAG}.log
 if [ -n "$KRE" ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KRE -s 2 -c 2 -f -o gpurun_out/prof_${TAG} \
-     python bench.py --frames 16 --steps 1 --warmup 3 --cpu-frames 0 --e2e-steps 0 --no-stage-pass > gpurun_out/ncu_full_${TAG}.log 2>&1
+  # one chunk of 16 frames launches 14 tiled kernels (raster_warp, down0, 5 down, 5 collapse, collapse0, unsharp)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s ${NCU_SKIP:-14} -c ${NCU_COUNT:-14} -f -o gpurun_out/prof_${TAG} \
+     python bench.py --frames 16 --steps 1 --warmup 1 --cpu-frames 0 --e2e-steps 0 --no-stage-pass > gpurun_out/ncu_full_${TAG}.log 2>&1
   tail -3 gpurun_out/ncu_full_${TAG}.log
 fi
