@@ -26,16 +26,18 @@ void launch_bgr_to_bgrx(cudaStream_t st, const uint8_t* bgr, uchar4* out, int w,
 // mask basis m2 = 1 - gray(gabor2)  (reference src/algo.cpp:250-252), rows `bpitch` floats apart
 void launch_mask_basis(cudaStream_t st, const float* gabor_bgr, float* m2, int bpitch, int w, int h);
 // paint_triangles + create_map + remap for both images, one CTA per 64x32 screen tile (reference src/algo.cpp:95-106,
-// 146-176, 232-238); warped rows are `wpitch` pixels apart; tri_map_out (nullable) receives frame 0's ID map
+// 146-176, 232-238). warped: per frame two planes of packed BGRX words (remap of image 1, of image 2), rows `wpitch`
+// words apart, `wstride` words per plane; tri_map_out (nullable) receives frame 0's ID map
 void launch_raster_warp(cudaStream_t st, const TriRaster* rast, const TriInverse* inv, const FrameParams* fp, int max_tri,
                         const int* tile_off, const int* tile_list, int cap, const int* overflow, const uchar4* src1,
-                        const uchar4* src2, uint2* warped, int wpitch, int* tri_map_out, int w, int h, int frames);
+                        const uchar4* src2, uint32_t* warped, int wpitch, size_t wstride, int* tri_map_out, int w, int h,
+                        int frames);
 
 // ---- kernels_pyramid.cu ------------------------------------------------------------------------------------------
 // level 0 -> 1: sources are the warped 8-bit pair (converted on the fly, algo.cpp:247-248) and the frame's blend
 // mask evaluated from the mask basis (algo.cpp:255-258); the level-0 mask is also kept in mask0 (per-frame planes,
 // rows bpitch floats apart, m0stride floats per frame) for launch_collapse0
-void launch_pyr_down0(cudaStream_t st, const uint2* warped, int wpitch, const float* basis, int bpitch,
+void launch_pyr_down0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* basis, int bpitch,
                       const FrameParams* fp, int w, int h, float* mask0, size_t m0stride, float* dst, LevelDesc dl,
                       int frames);
 // level k -> k+1 for the 7 planes (left BGR, right BGR, mask)
@@ -46,9 +48,9 @@ void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* 
 void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
                      LevelDesc cl, float* out_fine, int frames);
 // same for level 0, whose Gaussian level is the warped 8-bit pair + the level-0 mask planes
-void launch_collapse0(cudaStream_t st, const uint2* warped, int wpitch, const float* mask0, int mpitch, size_t m0stride,
-                      int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl, float* out_fine,
-                      LevelDesc ol, int frames);
+void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
+                      size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
+                      float* out_fine, LevelDesc ol, int frames);
 
 // ---- kernels_unsharp.cu ------------------------------------------------------------------------------------------
 // unsharp_mask(lapBlend, 1, amount, 0.3) + convertTo(CV_8U, 255)   (reference src/algo.cpp:263-265, util.cpp:113-148)

@@ -12,9 +12,11 @@
 //                      one warp per colour channel                reference src/blend.hpp:45-77; pyramids.cpp:903-1005
 //
 // Design (B200: the path is bound by instruction issue, not by HBM): no shared memory and no barriers.
-// A thread owns 4 adjacent output columns and walks down a run of rows; the separable filters keep their row-pass
+// A thread owns a few adjacent output columns and walks down a run of rows; the separable filters keep their row-pass
 // results in a register window that slides with the walk, so every source row is filtered horizontally once per
-// thread column. Work that shares source pixels but not arithmetic (the colour channels / the two images / the mask)
+// thread column, and the loads of the next step are issued before the current step is computed (software pipeline).
+// Global loads are laid out so that a warp instruction reads contiguous 16-byte pieces; taps shared with the
+// neighbouring lanes travel by warp shuffle. Work that shares source pixels but not arithmetic (the colour channels / the two images / the mask)
 // is split across the warps of a CTA ("roles") so that the sliding windows stay small and the shared loads hit L1.
 // Every kernel body exists twice: an INTERIOR instantiation (no border logic at all, vector loads only, the
 // reference's vector-body association everywhere) and a generic one (cv::borderInterpolate on every tap, association
@@ -68,9 +70,9 @@ struct DownSel {
     __device__ __forceinline__ bool v1(int x) const { return x < v_end1; }
 };
 
-constexpr int DN_R = 16;          // output rows per warp of the pyrDown kernels (a warp covers 128 output columns)
+constexpr int DN_R = 16;          // output rows per warp of the pyrDown kernels
 
-// Per-thread association flags of the 4 output columns x..x+3 of one plane kind (bit i: vector-body association).
+// Per-thread association flags of 4 adjacent output columns x..x+3 of one plane kind (bit i: vector-body association).
 struct DownFlags { unsigned h, v; };
 __device__ __forceinline__ DownFlags down_flags(const DownSel& sel, int x, bool three, int ch) {
     DownFlags f{0u, 0u};
@@ -86,7 +88,7 @@ __device__ __forceinline__ bool down_lane_interior(int x, int sw, int dw, DownFl
     return x + 3 < dw && 2 * x - 2 >= 0 && 2 * x + 8 <= sw - 1 && f.h == 15u && f.v == 15u;
 }
 
-// row pass of the 4 outputs from the 11 taps s[2x-2 .. 2x+8]
+// row pass of 4 adjacent outputs from the 11 taps s[2x-2 .. 2x+8]
 template <bool INTERIOR>
 __device__ __forceinline__ void h5x4(const float (&t)[11], unsigned hflags, float (&o)[4]) {
 #pragma unroll
@@ -105,47 +107,95 @@ __device__ __forceinline__ float4 v5x4(const float (&r0)[4], const float (&r1)[4
 }
 
 // ---- level k -> k+1, float planes -----------------------------------------------------------------------------------
-template <bool INTERIOR>
-__device__ __forceinline__ void down_row_f32(const float* __restrict__ plane, int spitch, int sw, int sh, int iy, int x,
-                                             unsigned hflags, float (&o)[4]) {
-    float t[11];
-    if (INTERIOR) {
-        const float* __restrict__ p = plane + (size_t)iy * spitch + 2 * x;
-        const float2 a = __ldg(reinterpret_cast<const float2*>(p - 2));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p));
-        const float4 c = __ldg(reinterpret_cast<const float4*>(p + 4));
-        t[0] = a.x; t[1] = a.y; t[2] = b.x; t[3] = b.y; t[4] = b.z; t[5] = b.w; t[6] = c.x; t[7] = c.y; t[8] = c.z; t[9] = c.w;
-        t[10] = __ldg(p + 8);
-    } else {
-        const float* __restrict__ row = plane + (size_t)reflect101(iy, sh) * spitch;
-#pragma unroll
-        for (int j = 0; j < 11; ++j) t[j] = __ldg(row + reflect101(2 * x - 2 + j, sw));
-    }
-    h5x4<INTERIOR>(t, hflags, o);
-}
+// A warp covers 128 output columns as two chunks of 64; in chunk j lane l produces outputs xo = X0 + 64j + 2l, xo+1.
+// Its own four source values s[2xo .. 2xo+3] are one perfectly coalesced 128-bit load (lane stride 16 bytes); the taps it
+// shares with its neighbours (s[2xo-2], s[2xo-1] from lane l-1, s[2xo+4] from lane l+1) arrive by shuffle, and the two
+// lanes at the chunk ends fetch theirs with one predicated load each.
+struct DownRaw { float4 own; float2 left; float right; };      // left/right: only lane 0 / lane 31 load them
 
 template <bool INTERIOR>
-__device__ __forceinline__ void down_body_f32(const float* __restrict__ sp, int sw, int sh, int spitch, float* __restrict__ dp,
-                                              int dh, int dpitch, int x, int y0, DownFlags fl) {
-    float h[7][4];
+__device__ __forceinline__ void down_load(const float* __restrict__ plane, int spitch, int sh, int iy, int xo, int lane,
+                                          DownRaw& r) {
+    if (INTERIOR) {
+        const float* __restrict__ p = plane + (size_t)iy * spitch + 2 * xo;
+        r.own = __ldg(reinterpret_cast<const float4*>(p));
+        if (lane == 0) r.left = __ldg(reinterpret_cast<const float2*>(p - 2));
+        if (lane == 31) r.right = __ldg(p + 4);
+    }
+}
+
+// row pass of outputs xo, xo+1 of source row iy
+template <bool INTERIOR>
+__device__ __forceinline__ float2 down_rowpass(const float* __restrict__ plane, int spitch, int sw, int sh, int iy, int xo,
+                                               int lane, const DownRaw& r, bool va, bool vb, bool has_b) {
+    if (INTERIOR) {
+        float l2 = __shfl_up_sync(FULL, r.own.z, 1), l1 = __shfl_up_sync(FULL, r.own.w, 1);
+        float r0 = __shfl_down_sync(FULL, r.own.x, 1);
+        if (lane == 0) { l2 = r.left.x; l1 = r.left.y; }
+        if (lane == 31) r0 = r.right;
+        return make_float2(h5_vec(l2, l1, r.own.x, r.own.y, r.own.z), h5_vec(r.own.x, r.own.y, r.own.z, r.own.w, r0));
+    } else {
+        const float* __restrict__ row = plane + (size_t)reflect101(iy, sh) * spitch;
+        float t[5];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) down_row_f32<INTERIOR>(sp, spitch, sw, sh, 2 * y0 - 2 + j, x, fl.h, h[j]);
+        for (int j = 0; j < 5; ++j) t[j] = __ldg(row + reflect101(2 * xo - 2 + j, sw));
+        float2 o;
+        o.x = va ? h5_vec(t[0], t[1], t[2], t[3], t[4]) : h5_sca(t[0], t[1], t[2], t[3], t[4]);
+        o.y = 0.f;
+        if (has_b) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) t[j] = __ldg(row + reflect101(2 * xo + j, sw));
+            o.y = vb ? h5_vec(t[0], t[1], t[2], t[3], t[4]) : h5_sca(t[0], t[1], t[2], t[3], t[4]);
+        }
+        return o;
+    }
+}
+
+// One chunk (64 output columns) x DN_R output rows of one plane. Flags: bit 0/1 = vector-body association of the row
+// pass at xo / xo+1, bit 2/3 = of the column pass.
+template <bool INTERIOR>
+__device__ __forceinline__ void down_chunk_f32(const float* __restrict__ sp, int sw, int sh, int spitch, float* __restrict__ dp,
+                                               int dw, int dh, int dpitch, int xo, int y0, int lane, unsigned flags) {
+    const bool ha = flags & 1u, hb = flags & 2u, va = flags & 4u, vb = flags & 8u, has_b = INTERIOR || xo + 1 < dw;
+    float2 h0, h1, h2, h3, h4;
+    DownRaw ra, rb;
+    down_load<INTERIOR>(sp, spitch, sh, 2 * y0 - 2, xo, lane, ra);
+    down_load<INTERIOR>(sp, spitch, sh, 2 * y0 - 1, xo, lane, rb);
+    h0 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y0 - 2, xo, lane, ra, ha, hb, has_b);
+    h1 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y0 - 1, xo, lane, rb, ha, hb, has_b);
+    down_load<INTERIOR>(sp, spitch, sh, 2 * y0, xo, lane, ra);
+    h2 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y0, xo, lane, ra, ha, hb, has_b);
+    // software pipeline: the two source rows of output row y+1 are requested before output row y is computed
+    down_load<INTERIOR>(sp, spitch, sh, 2 * y0 + 1, xo, lane, ra);
+    down_load<INTERIOR>(sp, spitch, sh, 2 * y0 + 2, xo, lane, rb);
 #pragma unroll 1
-    for (int k = 0; k < DN_R; k += 2) {
+    for (int k = 0; k < DN_R; ++k) {
         const int y = y0 + k;
         if (!INTERIOR && y >= dh) break;
-        const bool two = INTERIOR || y + 1 < dh;
-        down_row_f32<INTERIOR>(sp, spitch, sw, sh, 2 * y + 1, x, fl.h, h[3]);
-        down_row_f32<INTERIOR>(sp, spitch, sw, sh, 2 * y + 2, x, fl.h, h[4]);
-        if (two) {
-            down_row_f32<INTERIOR>(sp, spitch, sw, sh, 2 * y + 3, x, fl.h, h[5]);
-            down_row_f32<INTERIOR>(sp, spitch, sw, sh, 2 * y + 4, x, fl.h, h[6]);
+        h3 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y + 1, xo, lane, ra, ha, hb, has_b);
+        h4 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y + 2, xo, lane, rb, ha, hb, has_b);
+        if (k + 1 < DN_R) {
+            down_load<INTERIOR>(sp, spitch, sh, 2 * y + 3, xo, lane, ra);
+            down_load<INTERIOR>(sp, spitch, sh, 2 * y + 4, xo, lane, rb);
         }
-        *reinterpret_cast<float4*>(dp + (size_t)y * dpitch + x) = v5x4<INTERIOR>(h[0], h[1], h[2], h[3], h[4], fl.v);
-        if (two) *reinterpret_cast<float4*>(dp + (size_t)(y + 1) * dpitch + x) = v5x4<INTERIOR>(h[2], h[3], h[4], h[5], h[6], fl.v);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { h[0][i] = h[4][i]; h[1][i] = h[5][i]; h[2][i] = h[6][i]; }
+        float2 o;
+        o.x = (INTERIOR || va) ? v5_vec(h0.x, h1.x, h2.x, h3.x, h4.x) : v5_sca(h0.x, h1.x, h2.x, h3.x, h4.x);
+        o.y = (INTERIOR || vb) ? v5_vec(h0.y, h1.y, h2.y, h3.y, h4.y) : v5_sca(h0.y, h1.y, h2.y, h3.y, h4.y);
+        *reinterpret_cast<float2*>(dp + (size_t)y * dpitch + xo) = o;
+        h0 = h2; h1 = h3; h2 = h4;
     }
+}
+
+__device__ __forceinline__ unsigned down_pair_flags(const DownSel& sel, int xo, bool three, int ch) {
+    unsigned f = 0;
+    if (three ? sel.h3(xo) : sel.h1(xo)) f |= 1u;
+    if (three ? sel.h3(xo + 1) : sel.h1(xo + 1)) f |= 2u;
+    if (three ? sel.v3(xo, ch) : sel.v1(xo)) f |= 4u;
+    if (three ? sel.v3(xo + 1, ch) : sel.v1(xo + 1)) f |= 8u;
+    return f;
+}
+__device__ __forceinline__ bool down_pair_interior(int xo, int sw, int dw, unsigned flags) {
+    return xo + 1 < dw && 2 * xo - 2 >= 0 && 2 * xo + 4 <= sw - 1 && flags == 15u;
 }
 
 }  // namespace
@@ -155,100 +205,125 @@ __device__ __forceinline__ void down_body_f32(const float* __restrict__ sp, int 
 __global__ void __launch_bounds__(128)
 k_pyr_down_roll(const float* __restrict__ src, int sw, int sh, int spitch, size_t sstride, float* __restrict__ dst, int dw,
                 int dh, int dpitch, size_t dstride) {
-    const int job = blockIdx.z, p = job % 7;
-    const int x = blockIdx.x * 128 + 4 * threadIdx.x, y0 = (blockIdx.y * 4 + threadIdx.y) * DN_R;
+    const int job = blockIdx.z, p = job % 7, lane = threadIdx.x;
+    const int y0 = (blockIdx.y * 4 + threadIdx.y) * DN_R;
     if (y0 >= dh) return;
     const float* __restrict__ sp = src + (size_t)job * sstride;
     float* __restrict__ dp = dst + (size_t)job * dstride;
     const DownSel sel(sw, dw);
-    const DownFlags fl = down_flags(sel, x, p < 6, p % 3);
     const bool rows_in = 2 * y0 - 2 >= 0 && 2 * (y0 + DN_R - 1) + 2 <= sh - 1 && y0 + DN_R <= dh;
-    if (__all_sync(FULL, rows_in && down_lane_interior(x, sw, dw, fl))) {
-        down_body_f32<true>(sp, sw, sh, spitch, dp, dh, dpitch, x, y0, fl);
-    } else if (x < dw) {
-        down_body_f32<false>(sp, sw, sh, spitch, dp, dh, dpitch, x, y0, fl);
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+        const int xo = blockIdx.x * 128 + 64 * j + 2 * lane;
+        const unsigned flags = down_pair_flags(sel, xo, p < 6, p % 3);
+        if (__all_sync(FULL, rows_in && down_pair_interior(xo, sw, dw, flags)))
+            down_chunk_f32<true>(sp, sw, sh, spitch, dp, dw, dh, dpitch, xo, y0, lane, flags);
+        else if (xo < dw)
+            down_chunk_f32<false>(sp, sw, sh, spitch, dp, dw, dh, dpitch, xo, y0, lane, flags);
     }
 }
 
 // ---- level 0 -> 1 -----------------------------------------------------------------------------------------------------
 namespace {
 
-// 11 source pixels 2x-2 .. 2x+8 of one warped row: the packed BGR word of image IMG (0: .x, 1: .y) of each
-template <bool INTERIOR, int IMG>
-__device__ __forceinline__ void load_words11(const uint2* __restrict__ wframe, int wpitch, int sw, int sh, int iy, int x,
-                                             uint32_t (&wd)[11]) {
+// Source row of level 0 for one role: 8 own values s[2x .. 2x+7] (two 128-bit loads, lane stride 32 bytes) and, for the
+// chunk-end lanes, the neighbours' values. T = uint32_t (packed BGRX words of one warped image) or float (mask basis).
+template <class T> struct Down0Raw { T own[8]; T left[2]; T right; };
+template <class T> struct Vec4Of;
+template <> struct Vec4Of<uint32_t> { typedef uint4 type; typedef uint2 half; };
+template <> struct Vec4Of<float> { typedef float4 type; typedef float2 half; };
+
+template <bool INTERIOR, class T>
+__device__ __forceinline__ void down0_load(const T* __restrict__ plane, int spitch, int iy, int x, int lane, Down0Raw<T>& r) {
     if (INTERIOR) {
-        const uint2* __restrict__ p = wframe + (size_t)iy * wpitch + 2 * x;
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p - 2));
-        wd[0] = IMG ? a.y : a.x; wd[1] = IMG ? a.w : a.z;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p + 2 * j));
-            wd[2 + 2 * j] = IMG ? b.y : b.x; wd[3 + 2 * j] = IMG ? b.w : b.z;
-        }
-        const uint2 c = __ldg(p + 8);
-        wd[10] = IMG ? c.y : c.x;
-    } else {
-        const uint2* __restrict__ row = wframe + (size_t)reflect101(iy, sh) * wpitch;
-#pragma unroll
-        for (int j = 0; j < 11; ++j) {
-            const uint2 q = __ldg(row + reflect101(2 * x - 2 + j, sw));
-            wd[j] = IMG ? q.y : q.x;
-        }
+        typedef typename Vec4Of<T>::type V4;
+        typedef typename Vec4Of<T>::half V2;
+        const T* __restrict__ p = plane + (size_t)iy * spitch + 2 * x;
+        const V4 a = __ldg(reinterpret_cast<const V4*>(p)), b = __ldg(reinterpret_cast<const V4*>(p + 4));
+        r.own[0] = a.x; r.own[1] = a.y; r.own[2] = a.z; r.own[3] = a.w; r.own[4] = b.x; r.own[5] = b.y; r.own[6] = b.z; r.own[7] = b.w;
+        if (lane == 0) { const V2 l = __ldg(reinterpret_cast<const V2*>(p - 2)); r.left[0] = l.x; r.left[1] = l.y; }
+        if (lane == 31) r.right = __ldg(p + 8);
     }
 }
 
-// roles 0..5: colour plane c of image IMG
-template <bool INTERIOR, int IMG>
-__device__ __forceinline__ void down0_body_img(const uint2* __restrict__ wframe, int wpitch, int sw, int sh, int c,
-                                               float* __restrict__ dp /* plane 3*IMG + c of the frame */, int dh, int dpitch,
-                                               int x, int y0, DownFlags fl) {
-    float h[7][4];
-    auto row = [&](int iy, int slot) {
-        uint32_t wd[11];
-        load_words11<INTERIOR, IMG>(wframe, wpitch, sw, sh, iy, x, wd);
-        float t[11];
+// the 11 taps s[2x-2 .. 2x+8] of the thread's 4 outputs
+template <bool INTERIOR, class T>
+__device__ __forceinline__ void down0_taps(const T* __restrict__ plane, int spitch, int sw, int sh, int iy, int x, int lane,
+                                           const Down0Raw<T>& r, T (&t)[11]) {
+    if (INTERIOR) {
+        T l2 = __shfl_up_sync(FULL, r.own[6], 1), l1 = __shfl_up_sync(FULL, r.own[7], 1);
+        T r0 = __shfl_down_sync(FULL, r.own[0], 1);
+        if (lane == 0) { l2 = r.left[0]; l1 = r.left[1]; }
+        if (lane == 31) r0 = r.right;
+        t[0] = l2; t[1] = l1;
 #pragma unroll
-        for (int j = 0; j < 11; ++j) t[j] = unit_from_byte(wd[j], c);
-        h5x4<INTERIOR>(t, fl.h, h[slot]);
+        for (int j = 0; j < 8; ++j) t[2 + j] = r.own[j];
+        t[10] = r0;
+    } else {
+        const T* __restrict__ row = plane + (size_t)reflect101(iy, sh) * spitch;
+#pragma unroll
+        for (int j = 0; j < 11; ++j) t[j] = __ldg(row + reflect101(2 * x - 2 + j, sw));
+    }
+}
+
+// roles 0 / 1: the three colour planes of one warped image (`words`: its packed BGRX plane). fl.h: row-pass flags;
+// fl.v: column-pass flags of the three channels, 4 bits each.
+template <bool INTERIOR>
+__device__ __forceinline__ void down0_body_img(const uint32_t* __restrict__ words, int wpitch, int sw, int sh,
+                                               float* __restrict__ dp /* first of the image's 3 planes */, size_t dstride, int dh,
+                                               int dpitch, int x, int y0, int lane, DownFlags fl) {
+    float h[3][5][4];
+    Down0Raw<uint32_t> ra, rb;
+    auto rowpass = [&](int iy, const Down0Raw<uint32_t>& r, int slot) {
+        uint32_t wd[11];
+        down0_taps<INTERIOR>(words, wpitch, sw, sh, iy, x, lane, r, wd);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float t[11];
+#pragma unroll
+            for (int j = 0; j < 11; ++j) t[j] = unit_from_byte(wd[j], c);
+            h5x4<INTERIOR>(t, fl.h, h[c][slot]);
+        }
     };
-    row(2 * y0 - 2, 0); row(2 * y0 - 1, 1); row(2 * y0, 2);
+    down0_load<INTERIOR>(words, wpitch, 2 * y0 - 2, x, lane, ra);
+    down0_load<INTERIOR>(words, wpitch, 2 * y0 - 1, x, lane, rb);
+    rowpass(2 * y0 - 2, ra, 0);
+    rowpass(2 * y0 - 1, rb, 1);
+    down0_load<INTERIOR>(words, wpitch, 2 * y0, x, lane, ra);
+    rowpass(2 * y0, ra, 2);
+    down0_load<INTERIOR>(words, wpitch, 2 * y0 + 1, x, lane, ra);
+    down0_load<INTERIOR>(words, wpitch, 2 * y0 + 2, x, lane, rb);
 #pragma unroll 1
-    for (int k = 0; k < DN_R; k += 2) {
+    for (int k = 0; k < DN_R; ++k) {
         const int y = y0 + k;
         if (!INTERIOR && y >= dh) break;
-        const bool two = INTERIOR || y + 1 < dh;
-        row(2 * y + 1, 3); row(2 * y + 2, 4);
-        if (two) { row(2 * y + 3, 5); row(2 * y + 4, 6); }
-        float* __restrict__ o = dp + (size_t)y * dpitch + x;
-        *reinterpret_cast<float4*>(o) = v5x4<INTERIOR>(h[0], h[1], h[2], h[3], h[4], fl.v);
-        if (two) *reinterpret_cast<float4*>(o + dpitch) = v5x4<INTERIOR>(h[2], h[3], h[4], h[5], h[6], fl.v);
+        rowpass(2 * y + 1, ra, 3);
+        rowpass(2 * y + 2, rb, 4);
+        if (k + 1 < DN_R) {
+            down0_load<INTERIOR>(words, wpitch, 2 * y + 3, x, lane, ra);
+            down0_load<INTERIOR>(words, wpitch, 2 * y + 4, x, lane, rb);
+        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { h[0][i] = h[4][i]; h[1][i] = h[5][i]; h[2][i] = h[6][i]; }
+        for (int c = 0; c < 3; ++c) {
+            *reinterpret_cast<float4*>(dp + (size_t)c * dstride + (size_t)y * dpitch + x) =
+                v5x4<INTERIOR>(h[c][0], h[c][1], h[c][2], h[c][3], h[c][4], (fl.v >> (4 * c)) & 15u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { h[c][0][i] = h[c][2][i]; h[c][1][i] = h[c][3][i]; h[c][2][i] = h[c][4][i]; }
+        }
     }
 }
 
-// role 6: the blend mask — evaluates lbmask from the mask basis, keeps it as the level-0 mask plane (own rows and
+// role 2: the blend mask — evaluates lbmask from the mask basis, keeps it as the level-0 mask plane (own rows and
 // columns only) and reduces it to level 1
 template <bool INTERIOR>
 __device__ __forceinline__ void down0_body_mask(const float* __restrict__ basis, int bpitch, double alpha, double beta, int sw,
                                                 int sh, float* __restrict__ mask0, float* __restrict__ dp, int dh, int dpitch,
-                                                int x, int y0, DownFlags fl) {
-    float h[7][4];
-    auto row = [&](int iy, int slot) {
+                                                int x, int y0, int lane, DownFlags fl) {
+    float h[5][4];
+    Down0Raw<float> ra, rb;
+    auto rowpass = [&](int iy, const Down0Raw<float>& r, int slot) {
         float t[11];
-        if (INTERIOR) {
-            const float* __restrict__ p = basis + (size_t)iy * bpitch + 2 * x;
-            const float2 a = __ldg(reinterpret_cast<const float2*>(p - 2));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p));
-            const float4 c = __ldg(reinterpret_cast<const float4*>(p + 4));
-            t[0] = a.x; t[1] = a.y; t[2] = b.x; t[3] = b.y; t[4] = b.z; t[5] = b.w; t[6] = c.x; t[7] = c.y; t[8] = c.z; t[9] = c.w;
-            t[10] = __ldg(p + 8);
-        } else {
-            const float* __restrict__ r = basis + (size_t)reflect101(iy, sh) * bpitch;
-#pragma unroll
-            for (int j = 0; j < 11; ++j) t[j] = __ldg(r + reflect101(2 * x - 2 + j, sw));
-        }
+        down0_taps<INTERIOR>(basis, bpitch, sw, sh, iy, x, lane, r, t);
 #pragma unroll
         for (int j = 0; j < 11; ++j) t[j] = blend_mask(t[j], alpha, beta);
         // level-0 mask plane: this thread owns source columns 2x .. 2x+7 of the source rows 2*y0 .. 2*y0 + 2*DN_R - 1
@@ -265,56 +340,63 @@ __device__ __forceinline__ void down0_body_mask(const float* __restrict__ basis,
         }
         h5x4<INTERIOR>(t, fl.h, h[slot]);
     };
-    row(2 * y0 - 2, 0); row(2 * y0 - 1, 1); row(2 * y0, 2);
+    down0_load<INTERIOR>(basis, bpitch, 2 * y0 - 2, x, lane, ra);
+    down0_load<INTERIOR>(basis, bpitch, 2 * y0 - 1, x, lane, rb);
+    rowpass(2 * y0 - 2, ra, 0);
+    rowpass(2 * y0 - 1, rb, 1);
+    down0_load<INTERIOR>(basis, bpitch, 2 * y0, x, lane, ra);
+    rowpass(2 * y0, ra, 2);
+    down0_load<INTERIOR>(basis, bpitch, 2 * y0 + 1, x, lane, ra);
+    down0_load<INTERIOR>(basis, bpitch, 2 * y0 + 2, x, lane, rb);
 #pragma unroll 1
-    for (int k = 0; k < DN_R; k += 2) {
+    for (int k = 0; k < DN_R; ++k) {
         const int y = y0 + k;
         if (!INTERIOR && y >= dh) break;
-        const bool two = INTERIOR || y + 1 < dh;
-        row(2 * y + 1, 3); row(2 * y + 2, 4);
-        if (two) { row(2 * y + 3, 5); row(2 * y + 4, 6); }
-        float* __restrict__ o = dp + (size_t)y * dpitch + x;
-        *reinterpret_cast<float4*>(o) = v5x4<INTERIOR>(h[0], h[1], h[2], h[3], h[4], fl.v);
-        if (two) *reinterpret_cast<float4*>(o + dpitch) = v5x4<INTERIOR>(h[2], h[3], h[4], h[5], h[6], fl.v);
+        rowpass(2 * y + 1, ra, 3);
+        rowpass(2 * y + 2, rb, 4);
+        if (k + 1 < DN_R) {
+            down0_load<INTERIOR>(basis, bpitch, 2 * y + 3, x, lane, ra);
+            down0_load<INTERIOR>(basis, bpitch, 2 * y + 4, x, lane, rb);
+        }
+        *reinterpret_cast<float4*>(dp + (size_t)y * dpitch + x) = v5x4<INTERIOR>(h[0], h[1], h[2], h[3], h[4], fl.v);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { h[0][i] = h[4][i]; h[1][i] = h[5][i]; h[2][i] = h[6][i]; }
+        for (int i = 0; i < 4; ++i) { h[0][i] = h[2][i]; h[1][i] = h[3][i]; h[2][i] = h[4][i]; }
     }
 }
 
 }  // namespace
 
-// block (32, 7): warp = role (0-2: image 1 B,G,R; 3-5: image 2 B,G,R; 6: mask); grid (ceil(dw/128), ceil(dh/16), frames).
-// warped: one uint2 per pixel (image 1 BGR in .x, image 2 BGR in .y), rows wpitch pixels apart. mask0: per-frame
-// level-0 mask planes (rows bpitch floats apart, plane stride m0stride) written here for k_collapse_roll<true>.
-__global__ void __launch_bounds__(224)
-k_pyr_down0_roll(const uint2* __restrict__ warped, int wpitch, const float* __restrict__ basis, int bpitch,
+// block (32, 3): warp = role (0: image 1, 1: image 2, 2: mask); grid (ceil(dw/128), ceil(dh/16), frames).
+// warped: per frame two planes of packed BGRX words (image 1, image 2), rows wpitch words apart, wstride words per
+// plane. mask0: per-frame level-0 mask planes (rows bpitch floats apart, m0stride floats per frame) written here for
+// k_collapse_roll<true>.
+__global__ void __launch_bounds__(96)
+k_pyr_down0_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride, const float* __restrict__ basis, int bpitch,
                  const FrameParams* __restrict__ fp, int sw, int sh, float* __restrict__ mask0, size_t m0stride,
                  float* __restrict__ dst, int dw, int dh, int dpitch, size_t dstride) {
-    const int f = blockIdx.z, role = threadIdx.y;
-    const int x = blockIdx.x * 128 + 4 * threadIdx.x, y0 = blockIdx.y * DN_R;
+    const int f = blockIdx.z, role = threadIdx.y, lane = threadIdx.x;
+    const int x = blockIdx.x * 128 + 4 * lane, y0 = blockIdx.y * DN_R;
     const DownSel sel(sw, dw);
     const bool rows_in = 2 * y0 - 2 >= 0 && 2 * (y0 + DN_R - 1) + 2 <= sh - 1 && y0 + DN_R <= dh;
-    float* __restrict__ dp = dst + ((size_t)f * 7 + role) * dstride;
-    if (role < 6) {
-        const int c = role % 3;
-        const DownFlags fl = down_flags(sel, x, true, c);
-        const uint2* __restrict__ wframe = warped + (size_t)f * sh * wpitch;
-        const bool interior = __all_sync(FULL, rows_in && down_lane_interior(x, sw, dw, fl));
-        if (role < 3) {
-            if (interior) down0_body_img<true, 0>(wframe, wpitch, sw, sh, c, dp, dh, dpitch, x, y0, fl);
-            else if (x < dw) down0_body_img<false, 0>(wframe, wpitch, sw, sh, c, dp, dh, dpitch, x, y0, fl);
-        } else {
-            if (interior) down0_body_img<true, 1>(wframe, wpitch, sw, sh, c, dp, dh, dpitch, x, y0, fl);
-            else if (x < dw) down0_body_img<false, 1>(wframe, wpitch, sw, sh, c, dp, dh, dpitch, x, y0, fl);
-        }
+    float* __restrict__ dframe = dst + (size_t)f * 7 * dstride;
+    if (role < 2) {
+        DownFlags fl = down_flags(sel, x, true, 0);
+        const unsigned v1 = down_flags(sel, x, true, 1).v, v2 = down_flags(sel, x, true, 2).v;
+        const bool lane_in = down_lane_interior(x, sw, dw, fl) && v1 == 15u && v2 == 15u;
+        fl.v |= (v1 << 4) | (v2 << 8);
+        const uint32_t* __restrict__ words = warped + ((size_t)f * 2 + role) * wstride;
+        if (__all_sync(FULL, rows_in && lane_in))
+            down0_body_img<true>(words, wpitch, sw, sh, dframe + (size_t)3 * role * dstride, dstride, dh, dpitch, x, y0, lane, fl);
+        else if (x < dw)
+            down0_body_img<false>(words, wpitch, sw, sh, dframe + (size_t)3 * role * dstride, dstride, dh, dpitch, x, y0, lane, fl);
     } else {
         const DownFlags fl = down_flags(sel, x, false, 0);
         const double alpha = fp[f].mask_alpha, beta = fp[f].mask_beta;
         float* __restrict__ m0 = mask0 + (size_t)f * m0stride;
         if (__all_sync(FULL, rows_in && down_lane_interior(x, sw, dw, fl)))
-            down0_body_mask<true>(basis, bpitch, alpha, beta, sw, sh, m0, dp, dh, dpitch, x, y0, fl);
+            down0_body_mask<true>(basis, bpitch, alpha, beta, sw, sh, m0, dframe + 6 * dstride, dh, dpitch, x, y0, lane, fl);
         else if (x < dw)
-            down0_body_mask<false>(basis, bpitch, alpha, beta, sw, sh, m0, dp, dh, dpitch, x, y0, fl);
+            down0_body_mask<false>(basis, bpitch, alpha, beta, sw, sh, m0, dframe + 6 * dstride, dh, dpitch, x, y0, lane, fl);
     }
 }
 
@@ -386,8 +468,8 @@ __device__ __forceinline__ float blend1(float gl, float gr, float m, float ul, f
 }
 
 struct CollapseArgs {
-    // fine level: L0 -> warped pair + level-0 mask plane; else the 7 Gaussian planes
-    const uint2* wframe; int wpitch;
+    // fine level: L0 -> the two warped word planes + level-0 mask plane; else the 7 Gaussian planes
+    const uint32_t* w1; const uint32_t* w2; int wpitch;
     const float* mask0; int mpitch;
     const float* gfine; int fpitch; size_t fstride;
     // coarse level
@@ -396,6 +478,52 @@ struct CollapseArgs {
     int w, h;
 };
 
+// raw loads of one software-pipeline stage (INTERIOR bodies only; the generic body loads where it consumes)
+struct UpRaw { float cm; float2 c01; float cp; };
+template <bool L0> struct FineRaw;
+template <> struct FineRaw<true> { uint4 a, b; float4 m; };      // 4 px of image 1, of image 2, mask
+template <> struct FineRaw<false> { float4 l, r, m; };
+
+__device__ __forceinline__ void up_load(const float* __restrict__ row, int fx, UpRaw& u) {
+    const float* __restrict__ p = row + (fx >> 1);
+    u.cm = __ldg(p - 1);
+    u.c01 = __ldg(reinterpret_cast<const float2*>(p));
+    u.cp = __ldg(p + 2);
+}
+__device__ __forceinline__ void up_row_raw(const UpRaw& u, float (&o)[4]) {
+    o[0] = __fmul_rn(__fadd_rn(__fadd_rn(u.cm, __fmul_rn(u.c01.x, 6.f)), u.c01.y), 1.f / 64);
+    o[1] = __fmul_rn(__fmul_rn(__fadd_rn(u.c01.x, u.c01.y), 4.f), 1.f / 64);
+    o[2] = __fmul_rn(__fadd_rn(__fadd_rn(u.c01.x, __fmul_rn(u.c01.y, 6.f)), u.cp), 1.f / 64);
+    o[3] = __fmul_rn(__fmul_rn(__fadd_rn(u.c01.y, u.cp), 4.f), 1.f / 64);
+}
+
+template <bool L0>
+__device__ __forceinline__ void fine_load(const CollapseArgs& A, int c, int fy, int fx, FineRaw<L0>& r);
+template <>
+__device__ __forceinline__ void fine_load<true>(const CollapseArgs& A, int c, int fy, int fx, FineRaw<true>& r) {
+    const size_t o = (size_t)fy * A.wpitch + fx;
+    r.a = __ldg(reinterpret_cast<const uint4*>(A.w1 + o));
+    r.b = __ldg(reinterpret_cast<const uint4*>(A.w2 + o));
+    r.m = __ldg(reinterpret_cast<const float4*>(A.mask0 + (size_t)fy * A.mpitch + fx));
+}
+template <>
+__device__ __forceinline__ void fine_load<false>(const CollapseArgs& A, int c, int fy, int fx, FineRaw<false>& r) {
+    const float* __restrict__ gp = A.gfine + (size_t)fy * A.fpitch + fx;
+    r.l = __ldg(reinterpret_cast<const float4*>(gp + (size_t)c * A.fstride));
+    r.r = __ldg(reinterpret_cast<const float4*>(gp + (size_t)(3 + c) * A.fstride));
+    r.m = __ldg(reinterpret_cast<const float4*>(gp + (size_t)6 * A.fstride));
+}
+__device__ __forceinline__ void fine_unpack(const FineRaw<true>& r, int c, float (&gl)[4], float (&gr)[4], float (&mk)[4]) {
+    gl[0] = unit_from_byte(r.a.x, c); gl[1] = unit_from_byte(r.a.y, c); gl[2] = unit_from_byte(r.a.z, c); gl[3] = unit_from_byte(r.a.w, c);
+    gr[0] = unit_from_byte(r.b.x, c); gr[1] = unit_from_byte(r.b.y, c); gr[2] = unit_from_byte(r.b.z, c); gr[3] = unit_from_byte(r.b.w, c);
+    mk[0] = r.m.x; mk[1] = r.m.y; mk[2] = r.m.z; mk[3] = r.m.w;
+}
+__device__ __forceinline__ void fine_unpack(const FineRaw<false>& r, int c, float (&gl)[4], float (&gr)[4], float (&mk)[4]) {
+    gl[0] = r.l.x; gl[1] = r.l.y; gl[2] = r.l.z; gl[3] = r.l.w;
+    gr[0] = r.r.x; gr[1] = r.r.y; gr[2] = r.r.z; gr[3] = r.r.w;
+    mk[0] = r.m.x; mk[1] = r.m.y; mk[2] = r.m.z; mk[3] = r.m.w;
+}
+
 // One warp = one colour channel c of a 128 x 32 fine tile.
 template <bool L0, bool INTERIOR>
 __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int fx, int cy0) {
@@ -403,44 +531,57 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
     const float* __restrict__ pr = A.gc + (size_t)(3 + c) * A.cstride;
     const float* __restrict__ po = A.oc + (size_t)c * A.cstride;
     float hm[3][4], h0[3][4], hp[3][4];          // row-pass values of coarse rows sy-1, sy, sy+1 for (left, right, out)
-    auto rows3 = [&](int cy, float (&h)[3][4]) {
+    UpRaw ru[3];
+    FineRaw<L0> rf[2];
+    auto coarse_load = [&](int cy) {
         const size_t off = (size_t)cy * A.cpitch;
-        up_row<INTERIOR>(pl + off, A.cw, A.w, fx, h[0]);
-        up_row<INTERIOR>(pr + off, A.cw, A.w, fx, h[1]);
-        up_row<INTERIOR>(po + off, A.cw, A.w, fx, h[2]);
+        up_load(pl + off, fx, ru[0]); up_load(pr + off, fx, ru[1]); up_load(po + off, fx, ru[2]);
     };
-    // borderInterpolate(2(sy-1), 2ch, REFLECT_101)/2: row -1 -> 1 (0 when the level has a single row)
-    rows3(INTERIOR ? cy0 - 1 : (cy0 >= 1 ? cy0 - 1 : (A.ch > 1 ? 1 : 0)), hm);
-    rows3(cy0, h0);
+    auto coarse_now = [&](int cy, float (&h)[3][4]) {            // generic: load where consumed
+        const size_t off = (size_t)cy * A.cpitch;
+        up_row<false>(pl + off, A.cw, A.w, fx, h[0]);
+        up_row<false>(pr + off, A.cw, A.w, fx, h[1]);
+        up_row<false>(po + off, A.cw, A.w, fx, h[2]);
+    };
+    if (INTERIOR) {
+        coarse_load(cy0 - 1);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) up_row_raw(ru[p], hm[p]);
+        coarse_load(cy0);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) up_row_raw(ru[p], h0[p]);
+        coarse_load(cy0 + 1);
+        fine_load<L0>(A, c, 2 * cy0, fx, rf[0]);
+        fine_load<L0>(A, c, 2 * cy0 + 1, fx, rf[1]);
+    } else {
+        // borderInterpolate(2(sy-1), 2ch, REFLECT_101)/2: row -1 -> 1 (0 when the level has a single row)
+        coarse_now(cy0 >= 1 ? cy0 - 1 : (A.ch > 1 ? 1 : 0), hm);
+        coarse_now(cy0, h0);
+    }
     float* __restrict__ orow = A.out + (size_t)c * A.ostride + (size_t)(2 * cy0) * A.opitch + fx;
 #pragma unroll 1
     for (int k = 0; k < CL_R; ++k) {
         const int sy = cy0 + k, fy = 2 * sy;
         if (!INTERIOR && fy >= A.h) break;
-        rows3(INTERIOR ? sy + 1 : min(sy + 1, A.ch - 1), hp);
         const bool two = INTERIOR || fy + 1 < A.h;
-        // fine Gaussian values of this channel and the mask, rows fy and fy+1
         float gl[2][4], gr[2][4], mk[2][4];
+        if (INTERIOR) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            if (r == 1 && !two) break;
-            if (L0) {
-                const uint2* __restrict__ wp = A.wframe + (size_t)(fy + r) * A.wpitch + fx;
-                const uint4 a = __ldg(reinterpret_cast<const uint4*>(wp)), b = __ldg(reinterpret_cast<const uint4*>(wp + 2));
-                gl[r][0] = unit_from_byte(a.x, c); gl[r][1] = unit_from_byte(a.z, c);
-                gl[r][2] = unit_from_byte(b.x, c); gl[r][3] = unit_from_byte(b.z, c);
-                gr[r][0] = unit_from_byte(a.y, c); gr[r][1] = unit_from_byte(a.w, c);
-                gr[r][2] = unit_from_byte(b.y, c); gr[r][3] = unit_from_byte(b.w, c);
-                const float4 m = __ldg(reinterpret_cast<const float4*>(A.mask0 + (size_t)(fy + r) * A.mpitch + fx));
-                mk[r][0] = m.x; mk[r][1] = m.y; mk[r][2] = m.z; mk[r][3] = m.w;
-            } else {
-                const float* __restrict__ gp = A.gfine + (size_t)(fy + r) * A.fpitch + fx;
-                const float4 l = __ldg(reinterpret_cast<const float4*>(gp + (size_t)c * A.fstride));
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(gp + (size_t)(3 + c) * A.fstride));
-                const float4 m = __ldg(reinterpret_cast<const float4*>(gp + (size_t)6 * A.fstride));
-                gl[r][0] = l.x; gl[r][1] = l.y; gl[r][2] = l.z; gl[r][3] = l.w;
-                gr[r][0] = rr.x; gr[r][1] = rr.y; gr[r][2] = rr.z; gr[r][3] = rr.w;
-                mk[r][0] = m.x; mk[r][1] = m.y; mk[r][2] = m.z; mk[r][3] = m.w;
+            for (int p = 0; p < 3; ++p) up_row_raw(ru[p], hp[p]);
+            fine_unpack(rf[0], c, gl[0], gr[0], mk[0]);
+            fine_unpack(rf[1], c, gl[1], gr[1], mk[1]);
+            if (k + 1 < CL_R) {                      // software pipeline: request the next step's rows now
+                coarse_load(sy + 2);
+                fine_load<L0>(A, c, fy + 2, fx, rf[0]);
+                fine_load<L0>(A, c, fy + 3, fx, rf[1]);
+            }
+        } else {
+            coarse_now(min(sy + 1, A.ch - 1), hp);
+            fine_load<L0>(A, c, fy, fx, rf[0]);
+            fine_unpack(rf[0], c, gl[0], gr[0], mk[0]);
+            if (two) {
+                fine_load<L0>(A, c, fy + 1, fx, rf[1]);
+                fine_unpack(rf[1], c, gl[1], gr[1], mk[1]);
             }
         }
         float e[4], o[4];
@@ -465,17 +606,18 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
 }  // namespace
 
 // block (32, 3): warp = colour channel; grid (ceil(w/128), ceil(h/32), frames).
-// L0: the fine Gaussian level is the warped 8-bit pair + the level-0 mask plane written by k_pyr_down0_roll.
+// L0: the fine Gaussian level is the warped 8-bit pair (two word planes per frame, wstride words each) + the level-0
+// mask plane written by k_pyr_down0_roll.
 template <bool L0>
 __global__ void __launch_bounds__(96)
-k_collapse_roll(const uint2* __restrict__ warped, int wpitch, const float* __restrict__ mask0, int mpitch, size_t m0stride,
-                const float* __restrict__ g_fine, int w, int h, int fpitch, size_t fstride, const float* __restrict__ g_coarse,
-                const float* __restrict__ out_coarse, int cw, int ch, int cpitch, size_t cstride, float* __restrict__ out_fine,
-                int opitch, size_t ostride) {
+k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride, const float* __restrict__ mask0, int mpitch,
+                size_t m0stride, const float* __restrict__ g_fine, int w, int h, int fpitch, size_t fstride,
+                const float* __restrict__ g_coarse, const float* __restrict__ out_coarse, int cw, int ch, int cpitch,
+                size_t cstride, float* __restrict__ out_fine, int opitch, size_t ostride) {
     const int f = blockIdx.z, c = threadIdx.y;
     const int fx = blockIdx.x * 128 + 4 * threadIdx.x, cy0 = blockIdx.y * CL_R;
     CollapseArgs A;
-    A.wframe = L0 ? warped + (size_t)f * h * wpitch : nullptr; A.wpitch = wpitch;
+    A.w1 = L0 ? warped + (size_t)f * 2 * wstride : nullptr; A.w2 = L0 ? A.w1 + wstride : nullptr; A.wpitch = wpitch;
     A.mask0 = L0 ? mask0 + (size_t)f * m0stride : nullptr; A.mpitch = mpitch;
     A.gfine = L0 ? nullptr : g_fine + (size_t)f * 7 * fstride; A.fpitch = fpitch; A.fstride = fstride;
     A.gc = g_coarse + (size_t)f * 7 * cstride; A.oc = out_coarse + (size_t)f * 3 * cstride;
@@ -489,11 +631,11 @@ k_collapse_roll(const uint2* __restrict__ warped, int wpitch, const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-void launch_pyr_down0(cudaStream_t st, const uint2* warped, int wpitch, const float* basis, int bpitch,
+void launch_pyr_down0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* basis, int bpitch,
                       const FrameParams* fp, int w, int h, float* mask0, size_t m0stride, float* dst, LevelDesc dl,
                       int frames) {
-    k_pyr_down0_roll<<<dim3(div_up(dl.w, 128), div_up(dl.h, DN_R), frames), dim3(32, 7), 0, st>>>(
-        warped, wpitch, basis, bpitch, fp, w, h, mask0, m0stride, dst, dl.w, dl.h, dl.pitch, dl.plane_stride);
+    k_pyr_down0_roll<<<dim3(div_up(dl.w, 128), div_up(dl.h, DN_R), frames), dim3(32, 3), 0, st>>>(
+        warped, wpitch, wstride, basis, bpitch, fp, w, h, mask0, m0stride, dst, dl.w, dl.h, dl.pitch, dl.plane_stride);
 }
 
 void launch_pyr_down(cudaStream_t st, const float* src, LevelDesc sl, float* dst, LevelDesc dl, int frames) {
@@ -508,15 +650,15 @@ void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* 
 void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
                      LevelDesc cl, float* out_fine, int frames) {
     k_collapse_roll<false><<<dim3(div_up(fl.w, 128), div_up(fl.h, 2 * CL_R), frames), dim3(32, 3), 0, st>>>(
-        nullptr, 0, nullptr, 0, 0, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
+        nullptr, 0, 0, nullptr, 0, 0, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
         cl.plane_stride, out_fine, fl.pitch, fl.plane_stride);
 }
 
-void launch_collapse0(cudaStream_t st, const uint2* warped, int wpitch, const float* mask0, int mpitch, size_t m0stride,
-                      int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl, float* out_fine,
-                      LevelDesc ol, int frames) {
+void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
+                      size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
+                      float* out_fine, LevelDesc ol, int frames) {
     k_collapse_roll<true><<<dim3(div_up(w, 128), div_up(h, 2 * CL_R), frames), dim3(32, 3), 0, st>>>(
-        warped, wpitch, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
+        warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
         cl.plane_stride, out_fine, ol.pitch, ol.plane_stride);
 }
 

@@ -102,7 +102,9 @@ struct UsThread {
 
 constexpr int US_XROW = 3 * US_XW, US_CROW = 3 * US_CW;      // floats per ring row (3 channels)
 
-// R: row pass of virtual row vb + 5 + warp, all three channels. SLOT-independent: the ring slot is passed in.
+// R: row pass of virtual row vb + 5 + warp, all three channels; the ring slot is passed in. INTERIOR (a CTA-uniform
+// property of the strip): every lane's taps lie inside the image and in the vector-body region, so no border logic.
+template <bool INTERIOR>
 __device__ __forceinline__ void us_row_pass(const UsThread& T, const float* __restrict__ img, int pitch, size_t stride,
                                             float* xs_row, float* rp_row, int v) {
     const float* __restrict__ row = img + (size_t)reflect101(v, T.h) * pitch + T.gx0;
@@ -110,14 +112,14 @@ __device__ __forceinline__ void us_row_pass(const UsThread& T, const float* __re
     for (int c = 0; c < 3; ++c, row += stride) {
         float* xrow = xs_row + c * US_XW;
         float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (T.in_img) {
+        if (INTERIOR || T.in_img) {
             own = __ldg(reinterpret_cast<const float4*>(row));
             *reinterpret_cast<float4*>(xrow + 4 + 4 * T.lane) = own;
         }
         if (T.halo) *reinterpret_cast<float4*>(xrow + T.halo_soff) = __ldg(reinterpret_cast<const float4*>(row + T.halo_goff));
         __syncwarp();
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (T.lane_fast) {
+        if (INTERIOR || T.lane_fast) {
             const float4 lft = *reinterpret_cast<const float4*>(xrow + 4 * T.lane);
             const float4 rgt = *reinterpret_cast<const float4*>(xrow + 8 + 4 * T.lane);
             const float t[12] = {lft.x, lft.y, lft.z, lft.w, own.x, own.y, own.z, own.w, rgt.x, rgt.y, rgt.z, rgt.w};
@@ -142,7 +144,7 @@ __device__ __forceinline__ void us_row_pass(const UsThread& T, const float* __re
 }
 
 // C: column pass + diff of rows vb+1+4*HF .. +3 for channel c; every ring slot is a compile-time constant.
-template <int PAR, int HF>
+template <bool INTERIOR, int PAR, int HF>
 __device__ __forceinline__ void us_col_pass(const UsThread& T, const float* rp_t, const float* xs_t, float* df_t,
                                             uint32_t* fl_c, int vb, int c) {
     constexpr int K0 = 8 * PAR + 4 * HF - 3;                 // window row j lives in ring slot (K0 + j) & 15
@@ -152,18 +154,17 @@ __device__ __forceinline__ void us_col_pass(const UsThread& T, const float* rp_t
     float4 win[12];
 #pragma unroll
     for (int j = 0; j < 12; ++j) win[j] = *reinterpret_cast<const float4*>(rp_t + ((K0 + j) & 15) * US_CROW);
-    const bool fused = 3 * (T.gx0 + 3) + c < T.tail_from;         // whole group in the vector body
+    const bool fused = INTERIOR || 3 * (T.gx0 + 3) + c < T.tail_from;         // whole group in the vector body
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        constexpr int dummy = 0; (void)dummy;
         const int slot = (K0 + 4 + i) & 15;
         const int v = v0 + i;
         if (v < lo || v > hi) continue;                            // warp-uniform
         float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
         bool big = false;
-        if (T.in_img) {
+        if (INTERIOR || T.in_img) {
             float4 b;
-            if (T.h == 1) {
+            if (!INTERIOR && T.h == 1) {
                 b = win[4 + i];
             } else if (fused) {
                 b.x = col9(win[i].x, win[i + 1].x, win[i + 2].x, win[i + 3].x, win[i + 4].x, win[i + 5].x, win[i + 6].x, win[i + 7].x, win[i + 8].x, true);
@@ -179,8 +180,8 @@ __device__ __forceinline__ void us_col_pass(const UsThread& T, const float* rp_t
             const float4 x = *reinterpret_cast<const float4*>(xs_t + slot * US_XROW);
             d = make_float4(__fsub_rn(x.x, b.x), __fsub_rn(x.y, b.y), __fsub_rn(x.z, b.z), __fsub_rn(x.w, b.w));
             // columns past the image hold padding: keep them out of the flags
-            const float m0 = fabsf(d.x), m1 = T.gx0 + 1 < T.w ? fabsf(d.y) : 0.f, m2 = T.gx0 + 2 < T.w ? fabsf(d.z) : 0.f,
-                        m3 = T.gx0 + 3 < T.w ? fabsf(d.w) : 0.f;
+            const float m0 = fabsf(d.x), m1 = (INTERIOR || T.gx0 + 1 < T.w) ? fabsf(d.y) : 0.f,
+                        m2 = (INTERIOR || T.gx0 + 2 < T.w) ? fabsf(d.z) : 0.f, m3 = (INTERIOR || T.gx0 + 3 < T.w) ? fabsf(d.w) : 0.f;
             big = !(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) < US_FLAG_T);
         }
         *reinterpret_cast<float4*>(df_t + slot * US_CROW) = d;
@@ -190,11 +191,11 @@ __device__ __forceinline__ void us_col_pass(const UsThread& T, const float* rp_t
 }
 
 // M: median / threshold / sharpen / 8-bit store of row vb + warp.
-template <int PAR>
+template <bool INTERIOR, int PAR>
 __device__ __forceinline__ void us_emit(const UsThread& T, const float* xs, const float* df, const uint32_t* fl, int vb,
                                         float amount, double norm_thr2, uint8_t* __restrict__ dst, bool dst_words) {
     const int y = vb + T.warp, gx = T.x0 + 4 * T.lane;
-    if (y >= T.Y1 || T.lane >= US_W / 4 || gx >= T.w) return;
+    if (y >= T.Y1 || T.lane >= US_W / 4 || (!INTERIOR && gx >= T.w)) return;
     const int ym = max(y - 1, 0), yp = min(y + 1, T.h - 1);
     const int sc = (8 * PAR + T.warp) & 15, sm = (sc + (ym - y)) & 15, sp = (sc + (yp - y)) & 15;
     // computed-column group of gx is lane+1; its 3x3 windows reach groups lane .. lane+2
@@ -206,7 +207,7 @@ __device__ __forceinline__ void us_emit(const UsThread& T, const float* xs, cons
 #pragma unroll
     for (int c = 0; c < 3; ++c) px[c] = *reinterpret_cast<const float4*>(xrow + c * US_XW);
     float v[3][4] = {{px[0].x, px[0].y, px[0].z, px[0].w}, {px[1].x, px[1].y, px[1].z, px[1].w}, {px[2].x, px[2].y, px[2].z, px[2].w}};
-    const int npx = min(4, T.w - gx);
+    const int npx = INTERIOR ? 4 : min(4, T.w - gx);
     if (flagged) {
 #pragma unroll 1
         for (int i = 0; i < npx; ++i) {
@@ -241,7 +242,7 @@ __device__ __forceinline__ void us_emit(const UsThread& T, const float* xs, cons
 #pragma unroll
         for (int i = 0; i < 4; ++i) q[c][i] = u8_magic(v[c][i]);
     uint8_t* drow = dst + ((size_t)y * T.w + gx) * 3;
-    if (dst_words && npx == 4) {
+    if (INTERIOR || (dst_words && npx == 4)) {
         uint32_t* d32 = reinterpret_cast<uint32_t*>(drow);
         d32[0] = pack_u8x4(q[0][0], q[1][0], q[2][0], q[0][1]);
         d32[1] = pack_u8x4(q[1][1], q[2][1], q[0][2], q[1][2]);
@@ -258,7 +259,7 @@ __device__ __forceinline__ void us_emit(const UsThread& T, const float* xs, cons
 
 // One step (8 rows) of the strip walk; PAR = step parity, which fixes every ring slot at compile time
 // (rows advance by 8 per step, the rings hold 16 rows).
-template <int PAR>
+template <bool INTERIOR, int PAR>
 __device__ __forceinline__ void us_step(const UsThread& T, int s, const float* __restrict__ img, int pitch, size_t stride,
                                         float* xs, float* rp, float* df, uint32_t* fl, float amount, double norm_thr2,
                                         uint8_t* __restrict__ dst, bool dst_words) {
@@ -267,7 +268,7 @@ __device__ __forceinline__ void us_step(const UsThread& T, int s, const float* _
         const int v = vb + 5 + T.warp;
         if (v >= T.Y0 - 5 && v <= T.Y1 + 4) {
             const int slot = (8 * PAR + 5 + T.warp) & 15;
-            us_row_pass(T, img, pitch, stride, xs + slot * US_XROW, rp + slot * US_CROW, v);
+            us_row_pass<INTERIOR>(T, img, pitch, stride, xs + slot * US_XROW, rp + slot * US_CROW, v);
         }
     }
     __syncthreads();
@@ -276,11 +277,11 @@ __device__ __forceinline__ void us_step(const UsThread& T, int s, const float* _
         const float* rp_t = rp + c * US_CW + 4 * T.lane;
         const float* xs_t = xs + c * US_XW + 4 + 4 * T.lane;
         float* df_t = df + c * US_CW + 4 * T.lane;
-        if (T.warp & 1) us_col_pass<PAR, 1>(T, rp_t, xs_t, df_t, fl + c, vb, c);
-        else us_col_pass<PAR, 0>(T, rp_t, xs_t, df_t, fl + c, vb, c);
+        if (T.warp & 1) us_col_pass<INTERIOR, PAR, 1>(T, rp_t, xs_t, df_t, fl + c, vb, c);
+        else us_col_pass<INTERIOR, PAR, 0>(T, rp_t, xs_t, df_t, fl + c, vb, c);
     }
     __syncthreads();
-    if (s >= 0) us_emit<PAR>(T, xs, df, fl, vb, amount, norm_thr2, dst, dst_words);
+    if (s >= 0) us_emit<INTERIOR, PAR>(T, xs, df, fl, vb, amount, norm_thr2, dst, dst_words);
     __syncthreads();
 }
 
@@ -316,9 +317,19 @@ k_unsharp_strip(const float* __restrict__ lap, int w, int h, int pitch, size_t s
     const bool dst_words = (w & 3) == 0 && ((size_t)dst & 3) == 0;
     const int n_steps = div_up(T.Y1 - T.Y0, US_STEP);
 
-    for (int s = -2; s < n_steps; s += 2) {
-        us_step<0>(T, s, img, pitch, stride, xs, rp, df, fl, P.amount, norm_thr2, dst, dst_words);
-        if (s + 1 < n_steps) us_step<1>(T, s + 1, img, pitch, stride, xs, rp, df, fl, P.amount, norm_thr2, dst, dst_words);
+    // strips whose 136 staged columns all lie inside the image, clear of the scalar-tail elements, with word-aligned
+    // output rows, run the INTERIOR instantiation (no horizontal border logic at all)
+    const bool interior = T.x0 - 8 >= 0 && T.x0 + 127 <= w - 1 && 3 * (T.x0 + 123) + 2 < T.tail_from && dst_words && h > 1;
+    if (interior) {
+        for (int s = -2; s < n_steps; s += 2) {
+            us_step<true, 0>(T, s, img, pitch, stride, xs, rp, df, fl, P.amount, norm_thr2, dst, dst_words);
+            if (s + 1 < n_steps) us_step<true, 1>(T, s + 1, img, pitch, stride, xs, rp, df, fl, P.amount, norm_thr2, dst, dst_words);
+        }
+    } else {
+        for (int s = -2; s < n_steps; s += 2) {
+            us_step<false, 0>(T, s, img, pitch, stride, xs, rp, df, fl, P.amount, norm_thr2, dst, dst_words);
+            if (s + 1 < n_steps) us_step<false, 1>(T, s + 1, img, pitch, stride, xs, rp, df, fl, P.amount, norm_thr2, dst, dst_words);
+        }
     }
 }
 

@@ -6,7 +6,7 @@
 //   frame ring        : max_batch_frames x [H][W*3] 8-bit BGR — the rendered frames stay in HBM until downloaded
 //   morphed points    : max_batch_frames x max_points float2
 //   chunk scratch (xB): FrameParams; triangle indices; TriInverse / TriRaster records; triangle-ID map int32 [H][W];
-//                       warped pair uint2 [H][pitch0]; Gaussian levels 1..L (7 planes); collapsed levels 0..L
+//                       warped pair 2 x uint32 BGRX [H][pitch0]; Gaussian levels 1..L (7 planes); collapsed levels 0..L
 //                       (3 planes); level-0 blend mask float [H][pitch0]
 #include <cuda_runtime.h>
 
@@ -65,7 +65,7 @@ struct poppy_cuda_ctx {
     int* d_trimap = nullptr;             // stage dumps only (keep_stages)
     int *d_tile_cnt = nullptr, *d_tile_off = nullptr, *d_tile_list = nullptr, *d_overflow = nullptr;
     int n_tiles = 0, list_cap = 0;
-    uint2* d_warped = nullptr;
+    uint32_t* d_warped = nullptr;        // per frame: remap of image 1, remap of image 2 (packed BGRX words)
     float *d_mask0 = nullptr, *d_g = nullptr, *d_o = nullptr;
     // pinned staging, double buffered
     FrameParams* h_fp[2] = {nullptr, nullptr};
@@ -140,7 +140,7 @@ int ensure_chunk(poppy_cuda_ctx* c) {
     CU_TRY(c, dmalloc(&c->d_tile_off, B * (c->n_tiles + 1)));
     CU_TRY(c, dmalloc(&c->d_tile_list, B * c->list_cap));
     CU_TRY(c, dmalloc(&c->d_overflow, B));
-    CU_TRY(c, dmalloc(&c->d_warped, B * c->padded_pixels()));
+    CU_TRY(c, dmalloc(&c->d_warped, B * 2 * c->padded_pixels()));
     CU_TRY(c, dmalloc(&c->d_mask0, B * c->padded_pixels()));
     CU_TRY(c, dmalloc(&c->d_g, B * c->g_floats));
     CU_TRY(c, dmalloc(&c->d_o, B * c->o_floats));
@@ -238,11 +238,12 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
     }
     {   Scope s(c, KC_WARP);
         launch_raster_warp(st, c->d_rast, c->d_inv, c->d_fp, c->max_tri, c->d_tile_off, c->d_tile_list, c->list_cap,
-                           c->d_overflow, src1, c->d_src2, c->d_warped, c->pitch0(), c->keep_stages ? c->d_trimap : nullptr,
+                           c->d_overflow, src1, c->d_src2, c->d_warped, c->pitch0(), c->padded_pixels(),
+                           c->keep_stages ? c->d_trimap : nullptr,
                            w, h, nb);
     }
     {   Scope s(c, KC_PYR_DOWN);
-        launch_pyr_down0(st, c->d_warped, c->pitch0(), c->d_mbasis, c->pitch0(), c->d_fp, w, h, c->d_mask0,
+        launch_pyr_down0(st, c->d_warped, c->pitch0(), c->padded_pixels(), c->d_mbasis, c->pitch0(), c->d_fp, w, h, c->d_mask0,
                          c->padded_pixels(), g_level(c, 1), c->lv[1], nb);
     }
     for (int k = 1; k < L; ++k) {
@@ -257,7 +258,7 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
         launch_collapse(st, g_level(c, k), c->lv[k], g_level(c, k + 1), o_level(c, k + 1), c->lv[k + 1], o_level(c, k), nb);
     }
     {   Scope s(c, KC_COLLAPSE);
-        launch_collapse0(st, c->d_warped, c->pitch0(), c->d_mask0, c->pitch0(), c->padded_pixels(), w, h, g_level(c, 1),
+        launch_collapse0(st, c->d_warped, c->pitch0(), c->padded_pixels(), c->d_mask0, c->pitch0(), c->padded_pixels(), w, h, g_level(c, 1),
                          o_level(c, 1), c->lv[1], o_level(c, 0), c->lv[0], nb);
     }
     {   Scope s(c, KC_UNSHARP);
@@ -604,12 +605,12 @@ int poppy_cuda_debug_read(poppy_cuda_ctx* c, int stage, int frame, void* dst, si
     case POPPY_STAGE_WARPED1:
     case POPPY_STAGE_WARPED2: {
         if (int rc = need(px * 3)) return rc;
-        std::vector<uint2> tmp(px);
-        CU_TRY(c, cudaMemcpy2D(tmp.data(), (size_t)w * 8, c->d_warped, (size_t)c->pitch0() * 8, (size_t)w * 8, h,
-                               cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> tmp(px);
+        const uint32_t* plane = c->d_warped + (stage == POPPY_STAGE_WARPED1 ? 0 : c->padded_pixels());
+        CU_TRY(c, cudaMemcpy2D(tmp.data(), (size_t)w * 4, plane, (size_t)c->pitch0() * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost));
         uint8_t* o = (uint8_t*)dst;
         for (size_t i = 0; i < px; ++i) {
-            uint32_t v = stage == POPPY_STAGE_WARPED1 ? tmp[i].x : tmp[i].y;
+            uint32_t v = tmp[i];
             o[3 * i] = v & 255; o[3 * i + 1] = (v >> 8) & 255; o[3 * i + 2] = (v >> 16) & 255;
         }
         return 0;
