@@ -467,6 +467,29 @@ __device__ __forceinline__ float blend1(float gl, float gr, float m, float ul, f
     return __fadd_rn(uo, __fadd_rn(__fmul_rn(lap_l, m), __fmul_rn(lap_r, __fsub_rn(1.f, m))));
 }
 
+// ---- cp.async (LDGSTS) staging of the collapse kernel's loads -----------------------------------------------------------
+// The walk down a tile is latency bound if a thread only has one step of loads in flight, and a deeper register
+// prefetch costs occupancy. Instead every thread copies the loads of the next CL_STAGES steps asynchronously into its
+// own shared-memory slots (no register staging, no barriers: a thread only ever reads what it copied itself, so
+// cp.async.wait_group is the only synchronisation).
+constexpr int CL_STAGES = 2;
+struct __align__(16) CollapseStage {       // one step of one warp
+    float4 fine[6][32];                    // rows fy, fy+1: L0 -> (image 1 words, image 2 words, mask) x 2; else (left, right, mask) x 2
+    float2 c01[3][32];                     // coarse row sy+1 of (left, right, out): columns a, a+1
+    float cm[3][32];                       //                                         column a-1
+    float cp[3][32];                       //                                         column a+2
+};
+constexpr size_t CL_SMEM = sizeof(CollapseStage) * CL_STAGES * 3;
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 struct CollapseArgs {
     // fine level: L0 -> the two warped word planes + level-0 mask plane; else the 7 Gaussian planes
     const uint32_t* w1; const uint32_t* w2; int wpitch;
@@ -524,35 +547,64 @@ __device__ __forceinline__ void fine_unpack(const FineRaw<false>& r, int c, floa
     mk[0] = r.m.x; mk[1] = r.m.y; mk[2] = r.m.z; mk[3] = r.m.w;
 }
 
-// One warp = one colour channel c of a 128 x 32 fine tile.
+__device__ __forceinline__ void fine_from_stage(const CollapseStage& S, int r, int lane, FineRaw<true>& f) {
+    const float4 a = S.fine[3 * r + 0][lane], b = S.fine[3 * r + 1][lane];
+    f.a = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+    f.b = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+    f.m = S.fine[3 * r + 2][lane];
+}
+__device__ __forceinline__ void fine_from_stage(const CollapseStage& S, int r, int lane, FineRaw<false>& f) {
+    f.l = S.fine[3 * r + 0][lane]; f.r = S.fine[3 * r + 1][lane]; f.m = S.fine[3 * r + 2][lane];
+}
+
+// One warp = one colour channel c of a 128 x 32 fine tile. `stages`: this warp's CL_STAGES staging slots.
 template <bool L0, bool INTERIOR>
-__device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int fx, int cy0) {
+__device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int fx, int cy0, CollapseStage* stages, int lane) {
     const float* __restrict__ pl = A.gc + (size_t)c * A.cstride;
     const float* __restrict__ pr = A.gc + (size_t)(3 + c) * A.cstride;
     const float* __restrict__ po = A.oc + (size_t)c * A.cstride;
     float hm[3][4], h0[3][4], hp[3][4];          // row-pass values of coarse rows sy-1, sy, sy+1 for (left, right, out)
-    UpRaw ru[3];
-    FineRaw<L0> rf[2];
-    auto coarse_load = [&](int cy) {
+    auto coarse_now = [&](int cy, float (&h)[3][4]) {            // load where consumed
         const size_t off = (size_t)cy * A.cpitch;
-        up_load(pl + off, fx, ru[0]); up_load(pr + off, fx, ru[1]); up_load(po + off, fx, ru[2]);
+        up_row<INTERIOR>(pl + off, A.cw, A.w, fx, h[0]);
+        up_row<INTERIOR>(pr + off, A.cw, A.w, fx, h[1]);
+        up_row<INTERIOR>(po + off, A.cw, A.w, fx, h[2]);
     };
-    auto coarse_now = [&](int cy, float (&h)[3][4]) {            // generic: load where consumed
-        const size_t off = (size_t)cy * A.cpitch;
-        up_row<false>(pl + off, A.cw, A.w, fx, h[0]);
-        up_row<false>(pr + off, A.cw, A.w, fx, h[1]);
-        up_row<false>(po + off, A.cw, A.w, fx, h[2]);
+    // request step k's loads (coarse row cy0+k+1, fine rows 2(cy0+k), 2(cy0+k)+1) into its staging slot
+    auto issue = [&](int k) {
+        if (k < CL_R) {
+            CollapseStage& S = stages[k % CL_STAGES];
+            const size_t coff = (size_t)(cy0 + k + 1) * A.cpitch + (fx >> 1);
+            const float* __restrict__ cpl[3] = {pl + coff, pr + coff, po + coff};
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                cp_async<4>(&S.cm[p][lane], cpl[p] - 1);
+                cp_async<8>(&S.c01[p][lane], cpl[p]);
+                cp_async<4>(&S.cp[p][lane], cpl[p] + 2);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int fy = 2 * (cy0 + k) + r;
+                if (L0) {
+                    const size_t o = (size_t)fy * A.wpitch + fx;
+                    cp_async<16>(&S.fine[3 * r + 0][lane], A.w1 + o);
+                    cp_async<16>(&S.fine[3 * r + 1][lane], A.w2 + o);
+                    cp_async<16>(&S.fine[3 * r + 2][lane], A.mask0 + (size_t)fy * A.mpitch + fx);
+                } else {
+                    const float* __restrict__ gp = A.gfine + (size_t)fy * A.fpitch + fx;
+                    cp_async<16>(&S.fine[3 * r + 0][lane], gp + (size_t)c * A.fstride);
+                    cp_async<16>(&S.fine[3 * r + 1][lane], gp + (size_t)(3 + c) * A.fstride);
+                    cp_async<16>(&S.fine[3 * r + 2][lane], gp + (size_t)6 * A.fstride);
+                }
+            }
+        }
+        cp_async_commit();               // an empty group past the end keeps the group count uniform
     };
     if (INTERIOR) {
-        coarse_load(cy0 - 1);
 #pragma unroll
-        for (int p = 0; p < 3; ++p) up_row_raw(ru[p], hm[p]);
-        coarse_load(cy0);
-#pragma unroll
-        for (int p = 0; p < 3; ++p) up_row_raw(ru[p], h0[p]);
-        coarse_load(cy0 + 1);
-        fine_load<L0>(A, c, 2 * cy0, fx, rf[0]);
-        fine_load<L0>(A, c, 2 * cy0 + 1, fx, rf[1]);
+        for (int k = 0; k < CL_STAGES; ++k) issue(k);
+        coarse_now(cy0 - 1, hm);
+        coarse_now(cy0, h0);
     } else {
         // borderInterpolate(2(sy-1), 2ch, REFLECT_101)/2: row -1 -> 1 (0 when the level has a single row)
         coarse_now(cy0 >= 1 ? cy0 - 1 : (A.ch > 1 ? 1 : 0), hm);
@@ -566,22 +618,28 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
         const bool two = INTERIOR || fy + 1 < A.h;
         float gl[2][4], gr[2][4], mk[2][4];
         if (INTERIOR) {
+            cp_async_wait<CL_STAGES - 1>();
+            const CollapseStage& S = stages[k % CL_STAGES];
 #pragma unroll
-            for (int p = 0; p < 3; ++p) up_row_raw(ru[p], hp[p]);
-            fine_unpack(rf[0], c, gl[0], gr[0], mk[0]);
-            fine_unpack(rf[1], c, gl[1], gr[1], mk[1]);
-            if (k + 1 < CL_R) {                      // software pipeline: request the next step's rows now
-                coarse_load(sy + 2);
-                fine_load<L0>(A, c, fy + 2, fx, rf[0]);
-                fine_load<L0>(A, c, fy + 3, fx, rf[1]);
+            for (int p = 0; p < 3; ++p) {
+                UpRaw u;
+                u.cm = S.cm[p][lane]; u.c01 = S.c01[p][lane]; u.cp = S.cp[p][lane];
+                up_row_raw(u, hp[p]);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                FineRaw<L0> rf;
+                fine_from_stage(S, r, lane, rf);
+                fine_unpack(rf, c, gl[r], gr[r], mk[r]);
             }
         } else {
+            FineRaw<L0> rf;
             coarse_now(min(sy + 1, A.ch - 1), hp);
-            fine_load<L0>(A, c, fy, fx, rf[0]);
-            fine_unpack(rf[0], c, gl[0], gr[0], mk[0]);
+            fine_load<L0>(A, c, fy, fx, rf);
+            fine_unpack(rf, c, gl[0], gr[0], mk[0]);
             if (two) {
-                fine_load<L0>(A, c, fy + 1, fx, rf[1]);
-                fine_unpack(rf[1], c, gl[1], gr[1], mk[1]);
+                fine_load<L0>(A, c, fy + 1, fx, rf);
+                fine_unpack(rf, c, gl[1], gr[1], mk[1]);
             }
         }
         float e[4], o[4];
@@ -596,6 +654,7 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
         *reinterpret_cast<float4*>(orow) = make_float4(e[0], e[1], e[2], e[3]);
         if (two) *reinterpret_cast<float4*>(orow + A.opitch) = make_float4(o[0], o[1], o[2], o[3]);
         orow += 2 * (size_t)A.opitch;
+        if (INTERIOR) issue(k + CL_STAGES);           // the slot just consumed is free again
 #pragma unroll
         for (int p = 0; p < 3; ++p)
 #pragma unroll
@@ -609,11 +668,13 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
 // L0: the fine Gaussian level is the warped 8-bit pair (two word planes per frame, wstride words each) + the level-0
 // mask plane written by k_pyr_down0_roll.
 template <bool L0>
-__global__ void __launch_bounds__(96)
+__global__ void __launch_bounds__(96, 8)
 k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride, const float* __restrict__ mask0, int mpitch,
                 size_t m0stride, const float* __restrict__ g_fine, int w, int h, int fpitch, size_t fstride,
                 const float* __restrict__ g_coarse, const float* __restrict__ out_coarse, int cw, int ch, int cpitch,
                 size_t cstride, float* __restrict__ out_fine, int opitch, size_t ostride) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    CollapseStage* stages = reinterpret_cast<CollapseStage*>(smem_dyn) + CL_STAGES * threadIdx.y;
     const int f = blockIdx.z, c = threadIdx.y;
     const int fx = blockIdx.x * 128 + 4 * threadIdx.x, cy0 = blockIdx.y * CL_R;
     CollapseArgs A;
@@ -626,8 +687,8 @@ k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride,
     const int a = fx >> 1;
     const bool lane_in = a >= 1 && a + 2 <= cw - 1;                       // implies fx + 3 < w
     const bool rows_in = cy0 >= 1 && cy0 + CL_R <= ch - 1 && 2 * (cy0 + CL_R) <= h;
-    if (__all_sync(FULL, lane_in && rows_in)) collapse_body<L0, true>(A, c, fx, cy0);
-    else if (fx < w) collapse_body<L0, false>(A, c, fx, cy0);
+    if (__all_sync(FULL, lane_in && rows_in)) collapse_body<L0, true>(A, c, fx, cy0, stages, threadIdx.x);
+    else if (fx < w) collapse_body<L0, false>(A, c, fx, cy0, stages, threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -649,7 +710,12 @@ void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* 
 
 void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
                      LevelDesc cl, float* out_fine, int frames) {
-    k_collapse_roll<false><<<dim3(div_up(fl.w, 128), div_up(fl.h, 2 * CL_R), frames), dim3(32, 3), 0, st>>>(
+    static bool once = false;
+    if (!once) {
+        cudaFuncSetAttribute(k_collapse_roll<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM);
+        once = true;
+    }
+    k_collapse_roll<false><<<dim3(div_up(fl.w, 128), div_up(fl.h, 2 * CL_R), frames), dim3(32, 3), CL_SMEM, st>>>(
         nullptr, 0, 0, nullptr, 0, 0, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
         cl.plane_stride, out_fine, fl.pitch, fl.plane_stride);
 }
@@ -657,7 +723,12 @@ void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const f
 void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
                       size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
                       float* out_fine, LevelDesc ol, int frames) {
-    k_collapse_roll<true><<<dim3(div_up(w, 128), div_up(h, 2 * CL_R), frames), dim3(32, 3), 0, st>>>(
+    static bool once = false;
+    if (!once) {
+        cudaFuncSetAttribute(k_collapse_roll<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM);
+        once = true;
+    }
+    k_collapse_roll<true><<<dim3(div_up(w, 128), div_up(h, 2 * CL_R), frames), dim3(32, 3), CL_SMEM, st>>>(
         warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
         cl.plane_stride, out_fine, ol.pitch, ol.plane_stride);
 }

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -39,11 +40,11 @@ struct poppy_cuda_ctx {
     int device = 0, w = 0, h = 0, levels = 0, max_points = 0, max_tri = 0, max_frames = 0;
     int chunk = 0;            // frames per kernel batch (0 = not yet allocated)
     int want_chunk = 0;
-    bool keep_stages = false, stage_timing = false;
+    bool keep_stages = false, stage_timing = false, single_lane = false;
     bool have_pair = false, have_points = false;
     int n_points = 0, last_frames = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::string err;
     uint64_t launches = 0;
 
@@ -57,19 +58,24 @@ struct poppy_cuda_ctx {
     float2 *d_pts1_raw = nullptr, *d_pts2_raw = nullptr, *d_pts1 = nullptr, *d_pts2 = nullptr, *d_morphed = nullptr;
     uint8_t* d_frames = nullptr;
     unsigned long long* d_sum = nullptr;
-    // chunk scratch
-    FrameParams* d_fp = nullptr;
-    int3* d_tri = nullptr;
-    TriInverse* d_inv = nullptr;
-    TriRaster* d_rast = nullptr;
-    int* d_trimap = nullptr;             // stage dumps only (keep_stages)
-    int *d_tile_cnt = nullptr, *d_tile_off = nullptr, *d_tile_list = nullptr, *d_overflow = nullptr;
+    // Chunk scratch. Two lanes, each with its own stream and scratch: consecutive chunks of a direct-mode render go to
+    // alternating lanes, so the instruction-bound kernels of one chunk overlap the bandwidth-bound kernels of the other.
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev_staged = nullptr, ev_done = nullptr;
+        FrameParams* d_fp = nullptr;
+        int3* d_tri = nullptr;
+        TriInverse* d_inv = nullptr;
+        TriRaster* d_rast = nullptr;
+        int* d_trimap = nullptr;             // stage dumps only (keep_stages)
+        int *d_tile_cnt = nullptr, *d_tile_off = nullptr, *d_tile_list = nullptr, *d_overflow = nullptr;
+        uint32_t* d_warped = nullptr;        // per frame: remap of image 1, remap of image 2 (packed BGRX words)
+        float *d_mask0 = nullptr, *d_g = nullptr, *d_o = nullptr;
+        FrameParams* h_fp = nullptr;         // pinned staging
+        int32_t* h_tri = nullptr;
+    } lane[2];
+    int n_lanes = 0;                         // lanes allocated (0 = none yet)
     int n_tiles = 0, list_cap = 0;
-    uint32_t* d_warped = nullptr;        // per frame: remap of image 1, remap of image 2 (packed BGRX words)
-    float *d_mask0 = nullptr, *d_g = nullptr, *d_o = nullptr;
-    // pinned staging, double buffered
-    FrameParams* h_fp[2] = {nullptr, nullptr};
-    int32_t* h_tri[2] = {nullptr, nullptr};
 
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
@@ -104,14 +110,17 @@ int fail(poppy_cuda_ctx* c, int code, const char* fmt, ...) {
 template <class T> cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
 
 void free_chunk(poppy_cuda_ctx* c) {
-    cudaFree(c->d_fp); cudaFree(c->d_tri); cudaFree(c->d_inv); cudaFree(c->d_rast); cudaFree(c->d_trimap);
-    cudaFree(c->d_tile_cnt); cudaFree(c->d_tile_off); cudaFree(c->d_tile_list); cudaFree(c->d_overflow);
-    c->d_tile_cnt = nullptr; c->d_tile_off = nullptr; c->d_tile_list = nullptr; c->d_overflow = nullptr;
-    cudaFree(c->d_warped); cudaFree(c->d_mask0); cudaFree(c->d_g); cudaFree(c->d_o);
-    for (int i = 0; i < 2; ++i) { cudaFreeHost(c->h_fp[i]); cudaFreeHost(c->h_tri[i]); c->h_fp[i] = nullptr; c->h_tri[i] = nullptr; }
-    c->d_fp = nullptr; c->d_tri = nullptr; c->d_inv = nullptr; c->d_rast = nullptr; c->d_trimap = nullptr;
-    c->d_warped = nullptr; c->d_mask0 = nullptr; c->d_g = nullptr; c->d_o = nullptr;
+    for (auto& l : c->lane) {
+        cudaFree(l.d_fp); cudaFree(l.d_tri); cudaFree(l.d_inv); cudaFree(l.d_rast); cudaFree(l.d_trimap);
+        cudaFree(l.d_tile_cnt); cudaFree(l.d_tile_off); cudaFree(l.d_tile_list); cudaFree(l.d_overflow);
+        cudaFree(l.d_warped); cudaFree(l.d_mask0); cudaFree(l.d_g); cudaFree(l.d_o);
+        cudaFreeHost(l.h_fp); cudaFreeHost(l.h_tri);
+        cudaStream_t st = l.stream; cudaEvent_t e1 = l.ev_staged, e2 = l.ev_done;
+        l = poppy_cuda_ctx::Lane();
+        l.stream = st; l.ev_staged = e1; l.ev_done = e2;
+    }
     c->chunk = 0;
+    c->n_lanes = 0;
 }
 
 size_t per_frame_scratch_bytes(const poppy_cuda_ctx* c) {
@@ -122,39 +131,44 @@ size_t per_frame_scratch_bytes(const poppy_cuda_ctx* c) {
 int ensure_chunk(poppy_cuda_ctx* c) {
     int want = c->keep_stages ? 1 : c->want_chunk;
     if (want <= 0) {
-        // default: keep the chunk scratch under ~6 GiB and give the small pyramid levels enough CTAs
+        // default: keep a lane's scratch under ~6 GiB and give the small pyramid levels enough CTAs
         size_t per = per_frame_scratch_bytes(c);
         want = (int)std::min<size_t>(16, std::max<size_t>(1, (6ull << 30) / std::max<size_t>(per, 1)));
     }
     want = std::max(1, std::min(want, c->max_frames));
-    if (c->chunk == want) return 0;
+    // a second lane only pays when a render spans several chunks
+    const int lanes = (c->keep_stages || c->single_lane || want >= c->max_frames) ? 1 : 2;
+    if (c->chunk == want && c->n_lanes == lanes) return 0;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
+    for (auto& l : c->lane) if (l.stream) CU_TRY(c, cudaStreamSynchronize(l.stream));
     free_chunk(c);
     const size_t B = want;
-    CU_TRY(c, dmalloc(&c->d_fp, B));
-    CU_TRY(c, dmalloc(&c->d_tri, B * c->max_tri));
-    CU_TRY(c, dmalloc(&c->d_inv, B * c->max_tri));
-    CU_TRY(c, dmalloc(&c->d_rast, B * c->max_tri));
-    CU_TRY(c, dmalloc(&c->d_trimap, c->keep_stages ? c->pixels() : 1));
-    CU_TRY(c, dmalloc(&c->d_tile_cnt, B * c->n_tiles));
-    CU_TRY(c, dmalloc(&c->d_tile_off, B * (c->n_tiles + 1)));
-    CU_TRY(c, dmalloc(&c->d_tile_list, B * c->list_cap));
-    CU_TRY(c, dmalloc(&c->d_overflow, B));
-    CU_TRY(c, dmalloc(&c->d_warped, B * 2 * c->padded_pixels()));
-    CU_TRY(c, dmalloc(&c->d_mask0, B * c->padded_pixels()));
-    CU_TRY(c, dmalloc(&c->d_g, B * c->g_floats));
-    CU_TRY(c, dmalloc(&c->d_o, B * c->o_floats));
-    for (int i = 0; i < 2; ++i) {
-        CU_TRY(c, cudaMallocHost((void**)&c->h_fp[i], B * sizeof(FrameParams)));
-        CU_TRY(c, cudaMallocHost((void**)&c->h_tri[i], std::max<size_t>(B * c->max_tri, 1) * 3 * sizeof(int32_t)));
+    for (int i = 0; i < lanes; ++i) {
+        auto& l = c->lane[i];
+        CU_TRY(c, dmalloc(&l.d_fp, B));
+        CU_TRY(c, dmalloc(&l.d_tri, B * c->max_tri));
+        CU_TRY(c, dmalloc(&l.d_inv, B * c->max_tri));
+        CU_TRY(c, dmalloc(&l.d_rast, B * c->max_tri));
+        CU_TRY(c, dmalloc(&l.d_trimap, c->keep_stages ? c->pixels() : 1));
+        CU_TRY(c, dmalloc(&l.d_tile_cnt, B * c->n_tiles));
+        CU_TRY(c, dmalloc(&l.d_tile_off, B * (c->n_tiles + 1)));
+        CU_TRY(c, dmalloc(&l.d_tile_list, B * c->list_cap));
+        CU_TRY(c, dmalloc(&l.d_overflow, B));
+        CU_TRY(c, dmalloc(&l.d_warped, B * 2 * c->padded_pixels()));
+        CU_TRY(c, dmalloc(&l.d_mask0, B * c->padded_pixels()));
+        CU_TRY(c, dmalloc(&l.d_g, B * c->g_floats));
+        CU_TRY(c, dmalloc(&l.d_o, B * c->o_floats));
+        CU_TRY(c, cudaMallocHost((void**)&l.h_fp, B * sizeof(FrameParams)));
+        CU_TRY(c, cudaMallocHost((void**)&l.h_tri, std::max<size_t>(B * c->max_tri, 1) * 3 * sizeof(int32_t)));
     }
     c->chunk = want;
+    c->n_lanes = lanes;
     return 0;
 }
 
 // level k block of a chunk: all frames' planes of that level are contiguous
-float* g_level(poppy_cuda_ctx* c, int k) { return c->d_g + c->g_off[k] * c->chunk; }
-float* o_level(poppy_cuda_ctx* c, int k) { return c->d_o + c->o_off[k] * c->chunk; }
+float* g_level(poppy_cuda_ctx* c, const poppy_cuda_ctx::Lane& l, int k) { return l.d_g + c->g_off[k] * c->chunk; }
+float* o_level(poppy_cuda_ctx* c, const poppy_cuda_ctx::Lane& l, int k) { return l.d_o + c->o_off[k] * c->chunk; }
 
 cudaEvent_t get_event(poppy_cuda_ctx* c) {
     if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
@@ -164,14 +178,14 @@ cudaEvent_t get_event(poppy_cuda_ctx* c) {
 }
 
 struct Scope {   // counts a launch and, when stage timing is on, brackets it with events
-    poppy_cuda_ctx* c; int cls; TimedLaunch t{};
-    Scope(poppy_cuda_ctx* c_, int cls_) : c(c_), cls(cls_) {
+    poppy_cuda_ctx* c; int cls; cudaStream_t st; TimedLaunch t{};
+    Scope(poppy_cuda_ctx* c_, int cls_, cudaStream_t st_) : c(c_), cls(cls_), st(st_) {
         c->launches++;
         c->class_launches[cls]++;
-        if (c->stage_timing) { t.cls = cls; t.a = get_event(c); t.b = get_event(c); cudaEventRecord(t.a, c->stream); }
+        if (c->stage_timing) { t.cls = cls; t.a = get_event(c); t.b = get_event(c); cudaEventRecord(t.a, st); }
     }
     ~Scope() {
-        if (c->stage_timing) { cudaEventRecord(t.b, c->stream); c->timed.push_back(t); }
+        if (c->stage_timing) { cudaEventRecord(t.b, st); c->timed.push_back(t); }
     }
 };
 
@@ -186,11 +200,11 @@ void collect_timing(poppy_cuda_ctx* c) {
 }
 
 int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const double* mask, const int32_t* tri_idx,
-                 const int32_t* tri_off, bool chain, int slot) {
-    cudaStream_t st = c->stream;
-    CU_TRY(c, cudaEventSynchronize(c->ev_stage[slot]));       // staging buffers of this slot are free again
-    FrameParams* hp = c->h_fp[slot];
-    int32_t* ht = c->h_tri[slot];
+                 const int32_t* tri_off, bool chain, poppy_cuda_ctx::Lane& ln) {
+    cudaStream_t st = ln.stream;
+    CU_TRY(c, cudaEventSynchronize(ln.ev_staged));       // the lane's staging buffers are free again
+    FrameParams* hp = ln.h_fp;
+    int32_t* ht = ln.h_tri;
     int tri_total = 0, tri_max = 0;
     for (int i = 0; i < nb; ++i) {
         const int f = first + i;
@@ -213,9 +227,9 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
         tri_total += nt;
         tri_max = std::max(tri_max, nt);
     }
-    CU_TRY(c, cudaMemcpyAsync(c->d_fp, hp, nb * sizeof(FrameParams), cudaMemcpyHostToDevice, st));
-    if (tri_total) CU_TRY(c, cudaMemcpyAsync(c->d_tri, ht, (size_t)tri_total * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CU_TRY(c, cudaEventRecord(c->ev_stage[slot], st));
+    CU_TRY(c, cudaMemcpyAsync(ln.d_fp, hp, nb * sizeof(FrameParams), cudaMemcpyHostToDevice, st));
+    if (tri_total) CU_TRY(c, cudaMemcpyAsync(ln.d_tri, ht, (size_t)tri_total * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU_TRY(c, cudaEventRecord(ln.ev_staged, st));
 
     const bool chained = chain && first > 0;
     const float2* p1 = chained ? c->d_morphed + (size_t)(first - 1) * c->max_points : c->d_pts1;
@@ -223,49 +237,49 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
     float2* morphed = c->d_morphed + (size_t)first * c->max_points;
     const int n = c->n_points, w = c->w, h = c->h, L = c->levels;
 
-    {   Scope s(c, KC_POINTS);
-        launch_lerp_points(st, p1, 0, c->d_pts2, c->d_fp, morphed, c->max_points, n, nb, w, h);
+    {   Scope s(c, KC_POINTS, st);
+        launch_lerp_points(st, p1, 0, c->d_pts2, ln.d_fp, morphed, c->max_points, n, nb, w, h);
     }
-    CU_TRY(c, cudaMemsetAsync(c->d_tile_cnt, 0, (size_t)nb * c->n_tiles * sizeof(int), st));
-    {   Scope s(c, KC_GEOMETRY);
-        launch_tri_geometry(st, c->d_tri, c->d_fp, p1, 0, c->d_pts2, morphed, c->max_points, c->max_tri, tri_max, nb, w, h,
-                            c->d_inv, c->d_rast, c->d_tile_cnt);
+    CU_TRY(c, cudaMemsetAsync(ln.d_tile_cnt, 0, (size_t)nb * c->n_tiles * sizeof(int), st));
+    {   Scope s(c, KC_GEOMETRY, st);
+        launch_tri_geometry(st, ln.d_tri, ln.d_fp, p1, 0, c->d_pts2, morphed, c->max_points, c->max_tri, tri_max, nb, w, h,
+                            ln.d_inv, ln.d_rast, ln.d_tile_cnt);
     }
-    {   Scope s(c, KC_BIN);
+    {   Scope s(c, KC_BIN, st);
         c->launches++;          // scan + fill
-        launch_bin_triangles(st, c->d_rast, c->d_fp, c->max_tri, tri_max, nb, w, h, c->d_tile_cnt, c->d_tile_off,
-                             c->d_overflow, c->d_tile_list, c->list_cap);
+        launch_bin_triangles(st, ln.d_rast, ln.d_fp, c->max_tri, tri_max, nb, w, h, ln.d_tile_cnt, ln.d_tile_off,
+                             ln.d_overflow, ln.d_tile_list, c->list_cap);
     }
-    {   Scope s(c, KC_WARP);
-        launch_raster_warp(st, c->d_rast, c->d_inv, c->d_fp, c->max_tri, c->d_tile_off, c->d_tile_list, c->list_cap,
-                           c->d_overflow, src1, c->d_src2, c->d_warped, c->pitch0(), c->padded_pixels(),
-                           c->keep_stages ? c->d_trimap : nullptr,
+    {   Scope s(c, KC_WARP, st);
+        launch_raster_warp(st, ln.d_rast, ln.d_inv, ln.d_fp, c->max_tri, ln.d_tile_off, ln.d_tile_list, c->list_cap,
+                           ln.d_overflow, src1, c->d_src2, ln.d_warped, c->pitch0(), c->padded_pixels(),
+                           c->keep_stages ? ln.d_trimap : nullptr,
                            w, h, nb);
     }
-    {   Scope s(c, KC_PYR_DOWN);
-        launch_pyr_down0(st, c->d_warped, c->pitch0(), c->padded_pixels(), c->d_mbasis, c->pitch0(), c->d_fp, w, h, c->d_mask0,
-                         c->padded_pixels(), g_level(c, 1), c->lv[1], nb);
+    {   Scope s(c, KC_PYR_DOWN, st);
+        launch_pyr_down0(st, ln.d_warped, c->pitch0(), c->padded_pixels(), c->d_mbasis, c->pitch0(), ln.d_fp, w, h, ln.d_mask0,
+                         c->padded_pixels(), g_level(c, ln, 1), c->lv[1], nb);
     }
     for (int k = 1; k < L; ++k) {
-        Scope s(c, KC_PYR_DOWN);
-        launch_pyr_down(st, g_level(c, k), c->lv[k], g_level(c, k + 1), c->lv[k + 1], nb);
+        Scope s(c, KC_PYR_DOWN, st);
+        launch_pyr_down(st, g_level(c, ln, k), c->lv[k], g_level(c, ln, k + 1), c->lv[k + 1], nb);
     }
-    {   Scope s(c, KC_COLLAPSE);
-        launch_blend_coarsest(st, g_level(c, L), c->lv[L], o_level(c, L), nb);
+    {   Scope s(c, KC_COLLAPSE, st);
+        launch_blend_coarsest(st, g_level(c, ln, L), c->lv[L], o_level(c, ln, L), nb);
     }
     for (int k = L - 1; k >= 1; --k) {
-        Scope s(c, KC_COLLAPSE);
-        launch_collapse(st, g_level(c, k), c->lv[k], g_level(c, k + 1), o_level(c, k + 1), c->lv[k + 1], o_level(c, k), nb);
+        Scope s(c, KC_COLLAPSE, st);
+        launch_collapse(st, g_level(c, ln, k), c->lv[k], g_level(c, ln, k + 1), o_level(c, ln, k + 1), c->lv[k + 1], o_level(c, ln, k), nb);
     }
-    {   Scope s(c, KC_COLLAPSE);
-        launch_collapse0(st, c->d_warped, c->pitch0(), c->padded_pixels(), c->d_mask0, c->pitch0(), c->padded_pixels(), w, h, g_level(c, 1),
-                         o_level(c, 1), c->lv[1], o_level(c, 0), c->lv[0], nb);
+    {   Scope s(c, KC_COLLAPSE, st);
+        launch_collapse0(st, ln.d_warped, c->pitch0(), c->padded_pixels(), ln.d_mask0, c->pitch0(), c->padded_pixels(), w, h, g_level(c, ln, 1),
+                         o_level(c, ln, 1), c->lv[1], o_level(c, ln, 0), c->lv[0], nb);
     }
-    {   Scope s(c, KC_UNSHARP);
-        launch_unsharp_store(st, o_level(c, 0), c->lv[0], c->d_fp, c->d_frames, c->frame_bytes(), nb);
+    {   Scope s(c, KC_UNSHARP, st);
+        launch_unsharp_store(st, o_level(c, ln, 0), c->lv[0], ln.d_fp, c->d_frames, c->frame_bytes(), nb);
     }
     if (chain) {
-        Scope s(c, KC_MISC);
+        Scope s(c, KC_MISC, st);
         launch_bgr_to_bgrx(st, c->d_frames + (size_t)(first + nb - 1) * c->frame_bytes(), c->d_src_chain, w, h);
     }
     CU_TRY(c, cudaGetLastError());
@@ -301,6 +315,7 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
     poppy_cuda_ctx* c = new poppy_cuda_ctx();
     c->device = device; c->w = width; c->h = height; c->levels = pyramid_levels;
     c->max_points = max_points; c->max_tri = max_triangles; c->max_frames = max_batch_frames;
+    if (const char* e = std::getenv("POPPY_CUDA_SINGLE_LANE")) c->single_lane = e[0] == '1';   // A/B switch for profiling
     auto bail = [&](int rc) { g_create_error = c->err; poppy_cuda_destroy(c); return rc; };
 #define CR_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
         fail(c, POPPY_CUDA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(POPPY_CUDA_ERR_CUDA); } } while (0)
@@ -308,7 +323,11 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
     CR_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CR_TRY(cudaEventCreate(&c->ev_begin));
     CR_TRY(cudaEventCreate(&c->ev_end));
-    for (int i = 0; i < 2; ++i) CR_TRY(cudaEventCreateWithFlags(&c->ev_stage[i], cudaEventDisableTiming));
+    for (auto& l : c->lane) {
+        CR_TRY(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        CR_TRY(cudaEventCreateWithFlags(&l.ev_staged, cudaEventDisableTiming));
+        CR_TRY(cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming));
+    }
     // pyramid geometry: (n+1)/2 per level, 1x1 levels repeat (cv::pyrDown, pyramids.cpp:1260-1303)
     c->lv.resize(pyramid_levels + 1);
     c->g_off.assign(pyramid_levels + 2, 0);
@@ -353,6 +372,7 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& l : c->lane) if (l.stream) cudaStreamSynchronize(l.stream);
     collect_timing(c);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     free_chunk(c);
@@ -361,7 +381,11 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
     cudaFree(c->d_frames); cudaFree(c->d_sum);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
-    for (int i = 0; i < 2; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
+    for (auto& l : c->lane) {
+        if (l.ev_staged) cudaEventDestroy(l.ev_staged);
+        if (l.ev_done) cudaEventDestroy(l.ev_done);
+        if (l.stream) cudaStreamDestroy(l.stream);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -467,12 +491,20 @@ int poppy_cuda_render(poppy_cuda_ctx* c, int n_frames, const float* shape, const
     collect_timing(c);
     std::fill(c->class_ms, c->class_ms + KC_COUNT, 0.f);
     std::fill(c->class_launches, c->class_launches + KC_COUNT, 0ull);
+    // The context's stream brackets the render: the lanes start after everything queued on it so far (uploads, earlier
+    // renders, downloads) and it continues after both lanes are done.
     CU_TRY(c, cudaEventRecord(c->ev_begin, c->stream));
+    const int lanes = (chain || c->stage_timing) ? 1 : c->n_lanes;     // a chain is sequential; stage timing serialises
+    for (int i = 0; i < lanes; ++i) CU_TRY(c, cudaStreamWaitEvent(c->lane[i].stream, c->ev_begin, 0));
     const int B = chain ? 1 : c->chunk;
-    int slot = 0;
-    for (int first = 0; first < n_frames; first += B, slot ^= 1) {
+    int k = 0;
+    for (int first = 0; first < n_frames; first += B, ++k) {
         const int nb = std::min(B, n_frames - first);
-        if (int rc = render_chunk(c, first, nb, shape, mask, tri_idx, tri_off, chain != 0, slot)) return rc;
+        if (int rc = render_chunk(c, first, nb, shape, mask, tri_idx, tri_off, chain != 0, c->lane[k % lanes])) return rc;
+    }
+    for (int i = 0; i < lanes; ++i) {
+        CU_TRY(c, cudaEventRecord(c->lane[i].ev_done, c->lane[i].stream));
+        CU_TRY(c, cudaStreamWaitEvent(c->stream, c->lane[i].ev_done, 0));
     }
     CU_TRY(c, cudaEventRecord(c->ev_end, c->stream));
     c->last_frames = n_frames;
@@ -579,7 +611,7 @@ int poppy_cuda_debug_read(poppy_cuda_ctx* c, int stage, int frame, void* dst, si
     const size_t px = c->pixels();
     const int w = c->w, h = c->h;
     FrameParams P;
-    CU_TRY(c, cudaMemcpy(&P, c->d_fp, sizeof P, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(&P, c->lane[0].d_fp, sizeof P, cudaMemcpyDeviceToHost));
     auto need = [&](size_t want) -> int {
         return bytes == want ? 0 : fail(c, POPPY_CUDA_ERR_INVALID, "stage %d holds %zu bytes, caller gave %zu", stage, want, bytes);
     };
@@ -591,13 +623,13 @@ int poppy_cuda_debug_read(poppy_cuda_ctx* c, int stage, int frame, void* dst, si
         return 0;
     case POPPY_STAGE_TRI_MAP:
         if (int rc = need(px * 4)) return rc;
-        CU_TRY(c, cudaMemcpy(dst, c->d_trimap, bytes, cudaMemcpyDeviceToHost));
+        CU_TRY(c, cudaMemcpy(dst, c->lane[0].d_trimap, bytes, cudaMemcpyDeviceToHost));
         return 0;
     case POPPY_STAGE_INV_M1:
     case POPPY_STAGE_INV_M2: {
         if (int rc = need((size_t)P.n_tri * 36)) return rc;
         std::vector<TriInverse> tmp(std::max(P.n_tri, 1));
-        CU_TRY(c, cudaMemcpy(tmp.data(), c->d_inv, (size_t)P.n_tri * sizeof(TriInverse), cudaMemcpyDeviceToHost));
+        CU_TRY(c, cudaMemcpy(tmp.data(), c->lane[0].d_inv, (size_t)P.n_tri * sizeof(TriInverse), cudaMemcpyDeviceToHost));
         float* o = (float*)dst;
         for (int i = 0; i < P.n_tri; ++i) std::memcpy(o + 9 * i, stage == POPPY_STAGE_INV_M1 ? tmp[i].a : tmp[i].b, 36);
         return 0;
@@ -606,7 +638,7 @@ int poppy_cuda_debug_read(poppy_cuda_ctx* c, int stage, int frame, void* dst, si
     case POPPY_STAGE_WARPED2: {
         if (int rc = need(px * 3)) return rc;
         std::vector<uint32_t> tmp(px);
-        const uint32_t* plane = c->d_warped + (stage == POPPY_STAGE_WARPED1 ? 0 : c->padded_pixels());
+        const uint32_t* plane = c->lane[0].d_warped + (stage == POPPY_STAGE_WARPED1 ? 0 : c->padded_pixels());
         CU_TRY(c, cudaMemcpy2D(tmp.data(), (size_t)w * 4, plane, (size_t)c->pitch0() * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost));
         uint8_t* o = (uint8_t*)dst;
         for (size_t i = 0; i < px; ++i) {
@@ -617,13 +649,13 @@ int poppy_cuda_debug_read(poppy_cuda_ctx* c, int stage, int frame, void* dst, si
     }
     case POPPY_STAGE_MASK:
         if (int rc = need(px * 4)) return rc;
-        CU_TRY(c, cudaMemcpy2D(dst, (size_t)w * 4, c->d_mask0, (size_t)c->pitch0() * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost));
+        CU_TRY(c, cudaMemcpy2D(dst, (size_t)w * 4, c->lane[0].d_mask0, (size_t)c->pitch0() * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost));
         return 0;
     case POPPY_STAGE_LAP_BLEND: {
         if (int rc = need(px * 12)) return rc;
         const LevelDesc& d = c->lv[0];
         std::vector<float> tmp(3 * d.plane_stride);
-        CU_TRY(c, cudaMemcpy(tmp.data(), o_level(c, 0), tmp.size() * 4, cudaMemcpyDeviceToHost));
+        CU_TRY(c, cudaMemcpy(tmp.data(), o_level(c, c->lane[0], 0), tmp.size() * 4, cudaMemcpyDeviceToHost));
         float* o = (float*)dst;
         for (int y = 0; y < h; ++y)
             for (int x = 0; x < w; ++x)
