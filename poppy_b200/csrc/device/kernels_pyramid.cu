@@ -25,6 +25,8 @@
 // Bit-exactness: OpenCV's SSE-baseline vector bodies associate the 5-tap sums differently from the scalar code
 // that handles row borders and loop tails, so the association is selected per element position exactly as the
 // reference loops do (DownSel below); all adds and multiplies are individually rounded (no FMA contraction).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "pixel_ops.cuh"
@@ -364,18 +366,176 @@ __device__ __forceinline__ void down0_body_mask(const float* __restrict__ basis,
     }
 }
 
+
+// ---- TMA bulk-copy staging of the level 0 -> 1 kernel ----------------------------------------------------------------
+// The INTERIOR walk is bound by memory-level parallelism when its loads live in registers (one step ahead, ~2 KB in
+// flight per warp). Here every role warp owns a ring of D0_NS source-row segments in shared memory that its lane 0 keeps
+// full with cp.async.bulk (the 1-D form of TMA: one instruction per 1056-byte row segment, completion signalled on an
+// mbarrier), so ~8 KB per warp are in flight without holding a single register, and the walk itself only issues
+// shared-memory loads. A ring is private to its warp: the only synchronisation is the stage's mbarrier (data landed)
+// and a __syncwarp() before a consumed stage is refilled.
+constexpr int D0_NS = 8;                   // ring depth in source rows
+constexpr int D0_SEG = 264;                // elements per staged segment: source columns 2*X0 - 4 .. 2*X0 + 259
+constexpr int D0_ROWS = 2 * DN_R + 3;      // source rows 2*y0 - 2 .. 2*y0 + 2*DN_R of one walk
+struct __align__(128) Down0Ring {
+    uint32_t row[D0_NS][D0_SEG];
+    unsigned long long bar[D0_NS];
+};
+constexpr size_t D0_SMEM = sizeof(Down0Ring) * 3;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "POPPY_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra POPPY_MBAR_DONE;\n"
+        "bra POPPY_MBAR_WAIT;\n"
+        "POPPY_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (bytes: multiple of 16; both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Producer side of one warp's ring: `seg0` points at element (row 2*y0 - 2, column 2*X0 - 4) of the role's source plane.
+template <class T>
+struct Down0Feed {
+    Down0Ring* ring; const T* seg0; int pitch, lane;
+    __device__ __forceinline__ void issue(int r) const {           // lane 0 only
+        unsigned long long* bar = &ring->bar[r % D0_NS];
+        mbar_expect_tx(bar, D0_SEG * 4);
+        bulk_g2s(ring->row[r % D0_NS], seg0 + (size_t)r * pitch, D0_SEG * 4, bar);
+    }
+    __device__ __forceinline__ void start() const {
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < D0_NS; ++i) mbar_init(&ring->bar[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < D0_NS; ++r) issue(r);
+        }
+        __syncwarp();
+    }
+    // the 11 taps s[2x-2 .. 2x+8] of this lane's 4 outputs from staged row r (relative to 2*y0 - 2)
+    __device__ __forceinline__ void taps(int r, T (&t)[11]) const {
+        mbar_wait(&ring->bar[r % D0_NS], (unsigned)(r / D0_NS) & 1u);
+        const uint32_t* seg = ring->row[r % D0_NS] + 8 * lane;
+        const uint2 l = *reinterpret_cast<const uint2*>(seg + 2);
+        const uint4 a = *reinterpret_cast<const uint4*>(seg + 4), b = *reinterpret_cast<const uint4*>(seg + 8);
+        const uint32_t r0 = seg[12];
+        const uint32_t w[11] = {l.x, l.y, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, r0};
+#pragma unroll
+        for (int j = 0; j < 11; ++j) t[j] = *reinterpret_cast<const T*>(&w[j]);
+    }
+    // rows r0 .. r0 + n - 1 have been consumed by every lane: refill their stages with the rows D0_NS further down
+    __device__ __forceinline__ void refill(int r0, int n) const {
+        __syncwarp();
+        if (lane == 0) {
+            for (int r = r0 + D0_NS; r < r0 + n + D0_NS; ++r)
+                if (r < D0_ROWS) issue(r);
+        }
+    }
+};
+
+// roles 0 / 1, INTERIOR tiles, staged source
+__device__ __forceinline__ void down0_bulk_img(const Down0Feed<uint32_t>& F, float* __restrict__ dp, size_t dstride, int dpitch,
+                                               int x, int y0) {
+    float h[3][5][4];
+    auto rowpass = [&](int r, int slot) {
+        uint32_t wd[11];
+        F.taps(r, wd);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float t[11];
+#pragma unroll
+            for (int j = 0; j < 11; ++j) t[j] = unit_from_byte(wd[j], c);
+            h5x4<true>(t, 15u, h[c][slot]);
+        }
+    };
+    F.start();
+    rowpass(0, 0);
+    rowpass(1, 1);
+    rowpass(2, 2);
+    F.refill(0, 3);
+#pragma unroll 1
+    for (int k = 0; k < DN_R; ++k) {
+        const int y = y0 + k;
+        rowpass(2 * k + 3, 3);
+        rowpass(2 * k + 4, 4);
+        F.refill(2 * k + 3, 2);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            *reinterpret_cast<float4*>(dp + (size_t)c * dstride + (size_t)y * dpitch + x) =
+                v5x4<true>(h[c][0], h[c][1], h[c][2], h[c][3], h[c][4], 15u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { h[c][0][i] = h[c][2][i]; h[c][1][i] = h[c][3][i]; h[c][2][i] = h[c][4][i]; }
+        }
+    }
+}
+
+// role 2, INTERIOR tiles, staged mask basis
+__device__ __forceinline__ void down0_bulk_mask(const Down0Feed<float>& F, int bpitch, double alpha, double beta,
+                                                float* __restrict__ mask0, float* __restrict__ dp, int dpitch, int x, int y0) {
+    float h[5][4];
+    auto rowpass = [&](int r, int slot) {
+        float t[11];
+        F.taps(r, t);
+#pragma unroll
+        for (int j = 0; j < 11; ++j) t[j] = blend_mask(t[j], alpha, beta);
+        if (r >= 2 && r < 2 + 2 * DN_R) {          // source rows 2*y0 .. 2*y0 + 2*DN_R - 1: this warp owns their level-0 mask
+            float* __restrict__ m = mask0 + (size_t)(2 * y0 - 2 + r) * bpitch + 2 * x;
+            *reinterpret_cast<float4*>(m) = make_float4(t[2], t[3], t[4], t[5]);
+            *reinterpret_cast<float4*>(m + 4) = make_float4(t[6], t[7], t[8], t[9]);
+        }
+        h5x4<true>(t, 15u, h[slot]);
+    };
+    F.start();
+    rowpass(0, 0);
+    rowpass(1, 1);
+    rowpass(2, 2);
+    F.refill(0, 3);
+#pragma unroll 1
+    for (int k = 0; k < DN_R; ++k) {
+        const int y = y0 + k;
+        rowpass(2 * k + 3, 3);
+        rowpass(2 * k + 4, 4);
+        F.refill(2 * k + 3, 2);
+        *reinterpret_cast<float4*>(dp + (size_t)y * dpitch + x) = v5x4<true>(h[0], h[1], h[2], h[3], h[4], 15u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { h[0][i] = h[2][i]; h[1][i] = h[3][i]; h[2][i] = h[4][i]; }
+    }
+}
+
 }  // namespace
 
-// block (32, 3): warp = role (0: image 1, 1: image 2, 2: mask); grid (ceil(dw/128), ceil(dh/16), frames).
+// block (32, 3): three row groups of one role (0: image 1, 1: image 2, 2: mask); grid (ceil(dw/128), ceil(dh/48), 3 * frames).
 // warped: per frame two planes of packed BGRX words (image 1, image 2), rows wpitch words apart, wstride words per
 // plane. mask0: per-frame level-0 mask planes (rows bpitch floats apart, m0stride floats per frame) written here for
 // k_collapse_roll<true>.
+template <bool BULK>
 __global__ void __launch_bounds__(96)
 k_pyr_down0_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride, const float* __restrict__ basis, int bpitch,
                  const FrameParams* __restrict__ fp, int sw, int sh, float* __restrict__ mask0, size_t m0stride,
                  float* __restrict__ dst, int dw, int dh, int dpitch, size_t dstride) {
-    const int f = blockIdx.z, role = threadIdx.y, lane = threadIdx.x;
-    const int x = blockIdx.x * 128 + 4 * lane, y0 = blockIdx.y * DN_R;
+    extern __shared__ __align__(128) unsigned char smem_down0[];
+    // blockIdx.z = role * frames + f: CTAs that are resident together run the same role, i.e. the same hot loop, which
+    // keeps the per-scheduler instruction cache from thrashing between the (large, fully unrolled) role bodies. The three
+    // warps of a CTA take three consecutive row groups.
+    const int frames = gridDim.z / 3, role = blockIdx.z / frames, f = blockIdx.z - role * frames, lane = threadIdx.x;
+    const int X0 = blockIdx.x * 128, x = X0 + 4 * lane, y0 = (blockIdx.y * 3 + threadIdx.y) * DN_R;
+    if (y0 >= dh) return;
+    const int ring_slot = threadIdx.y;
     const DownSel sel(sw, dw);
     const bool rows_in = 2 * y0 - 2 >= 0 && 2 * (y0 + DN_R - 1) + 2 <= sh - 1 && y0 + DN_R <= dh;
     float* __restrict__ dframe = dst + (size_t)f * 7 * dstride;
@@ -385,18 +545,35 @@ k_pyr_down0_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride
         const bool lane_in = down_lane_interior(x, sw, dw, fl) && v1 == 15u && v2 == 15u;
         fl.v |= (v1 << 4) | (v2 << 8);
         const uint32_t* __restrict__ words = warped + ((size_t)f * 2 + role) * wstride;
-        if (__all_sync(FULL, rows_in && lane_in))
-            down0_body_img<true>(words, wpitch, sw, sh, dframe + (size_t)3 * role * dstride, dstride, dh, dpitch, x, y0, lane, fl);
-        else if (x < dw)
+        const bool interior = __all_sync(FULL, rows_in && lane_in) && (!BULK || (2 * X0 - 4 >= 0 && 2 * X0 - 4 + D0_SEG <= wpitch));
+        if (interior) {
+            if (BULK) {
+                const Down0Feed<uint32_t> F{reinterpret_cast<Down0Ring*>(smem_down0) + ring_slot,
+                                            words + (size_t)(2 * y0 - 2) * wpitch + 2 * X0 - 4, wpitch, lane};
+                down0_bulk_img(F, dframe + (size_t)3 * role * dstride, dstride, dpitch, x, y0);
+            } else {
+                down0_body_img<true>(words, wpitch, sw, sh, dframe + (size_t)3 * role * dstride, dstride, dh, dpitch, x, y0, lane, fl);
+            }
+        } else if (x < dw) {
             down0_body_img<false>(words, wpitch, sw, sh, dframe + (size_t)3 * role * dstride, dstride, dh, dpitch, x, y0, lane, fl);
+        }
     } else {
         const DownFlags fl = down_flags(sel, x, false, 0);
         const double alpha = fp[f].mask_alpha, beta = fp[f].mask_beta;
         float* __restrict__ m0 = mask0 + (size_t)f * m0stride;
-        if (__all_sync(FULL, rows_in && down_lane_interior(x, sw, dw, fl)))
-            down0_body_mask<true>(basis, bpitch, alpha, beta, sw, sh, m0, dframe + 6 * dstride, dh, dpitch, x, y0, lane, fl);
-        else if (x < dw)
+        const bool interior = __all_sync(FULL, rows_in && down_lane_interior(x, sw, dw, fl)) &&
+                              (!BULK || (2 * X0 - 4 >= 0 && 2 * X0 - 4 + D0_SEG <= bpitch));
+        if (interior) {
+            if (BULK) {
+                const Down0Feed<float> F{reinterpret_cast<Down0Ring*>(smem_down0) + ring_slot,
+                                         basis + (size_t)(2 * y0 - 2) * bpitch + 2 * X0 - 4, bpitch, lane};
+                down0_bulk_mask(F, bpitch, alpha, beta, m0, dframe + 6 * dstride, dpitch, x, y0);
+            } else {
+                down0_body_mask<true>(basis, bpitch, alpha, beta, sw, sh, m0, dframe + 6 * dstride, dh, dpitch, x, y0, lane, fl);
+            }
+        } else if (x < dw) {
             down0_body_mask<false>(basis, bpitch, alpha, beta, sw, sh, m0, dframe + 6 * dstride, dh, dpitch, x, y0, lane, fl);
+        }
     }
 }
 
@@ -692,11 +869,28 @@ k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// A/B switch for profiling: POPPY_CUDA_NO_BULK=1 selects the register-prefetch bodies everywhere
+static bool use_bulk() {
+    static const bool v = [] { const char* e = std::getenv("POPPY_CUDA_NO_BULK"); return !(e && e[0] == '1'); }();
+    return v;
+}
+
 void launch_pyr_down0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* basis, int bpitch,
                       const FrameParams* fp, int w, int h, float* mask0, size_t m0stride, float* dst, LevelDesc dl,
                       int frames) {
-    k_pyr_down0_roll<<<dim3(div_up(dl.w, 128), div_up(dl.h, DN_R), frames), dim3(32, 3), 0, st>>>(
-        warped, wpitch, wstride, basis, bpitch, fp, w, h, mask0, m0stride, dst, dl.w, dl.h, dl.pitch, dl.plane_stride);
+    const dim3 grid(div_up(dl.w, 128), div_up(dl.h, 3 * DN_R), 3 * frames), block(32, 3);
+    if (use_bulk()) {
+        static bool once = false;
+        if (!once) {
+            cudaFuncSetAttribute(k_pyr_down0_roll<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D0_SMEM);
+            once = true;
+        }
+        k_pyr_down0_roll<true><<<grid, block, D0_SMEM, st>>>(warped, wpitch, wstride, basis, bpitch, fp, w, h, mask0, m0stride, dst,
+                                                            dl.w, dl.h, dl.pitch, dl.plane_stride);
+    } else {
+        k_pyr_down0_roll<false><<<grid, block, 0, st>>>(warped, wpitch, wstride, basis, bpitch, fp, w, h, mask0, m0stride, dst,
+                                                        dl.w, dl.h, dl.pitch, dl.plane_stride);
+    }
 }
 
 void launch_pyr_down(cudaStream_t st, const float* src, LevelDesc sl, float* dst, LevelDesc dl, int frames) {

@@ -90,6 +90,11 @@ __device__ __forceinline__ float col9(float w0, float w1, float w2, float w3, fl
     return __fadd_rn(s, __fmul_rn(gk(4), __fadd_rn(w8, w0)));
 }
 
+__device__ __forceinline__ void us_cp_async16(float* smem_dst, const float* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
 // Per-thread constants of the strip kernel.
 struct UsThread {
     int w, h, lane, warp, gx0, x0, Y0, Y1, tail_from;
@@ -98,43 +103,59 @@ struct UsThread {
     bool halo;            // lane 0 / 1 stage the 4 columns left / right of the computed range
     int halo_goff;        // their offset from column gx0 in global memory ...
     int halo_soff;        // ... and their float offset in an input-ring row
+    int rfl_dst, rfl_src; // border strips: staged slot outside the image this lane fills, and the staged slot it mirrors (-1: none)
 };
 
 constexpr int US_XROW = 3 * US_XW, US_CROW = 3 * US_CW;      // floats per ring row (3 channels)
 
 // R: row pass of virtual row vb + 5 + warp, all three channels; the ring slot is passed in. INTERIOR (a CTA-uniform
 // property of the strip): every lane's taps lie inside the image and in the vector-body region, so no border logic.
+// All global loads of the row (3 channels, plus the halo groups of lanes 0/1) are issued before the first one is
+// consumed, so a warp exposes one memory latency per row instead of three. In border strips the staged columns that lie
+// outside the image are then filled by reflection from the staged row itself (BORDER_REFLECT_101), after which border
+// lanes run the same row filter as interior ones.
 template <bool INTERIOR>
 __device__ __forceinline__ void us_row_pass(const UsThread& T, const float* __restrict__ img, int pitch, size_t stride,
                                             float* xs_row, float* rp_row, int v) {
     const float* __restrict__ row = img + (size_t)reflect101(v, T.h) * pitch + T.gx0;
+    float4 own[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c, row += stride) {
-        float* xrow = xs_row + c * US_XW;
-        float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (INTERIOR || T.in_img) {
-            own = __ldg(reinterpret_cast<const float4*>(row));
-            *reinterpret_cast<float4*>(xrow + 4 + 4 * T.lane) = own;
-        }
-        if (T.halo) *reinterpret_cast<float4*>(xrow + T.halo_soff) = __ldg(reinterpret_cast<const float4*>(row + T.halo_goff));
-        __syncwarp();
+    for (int c = 0; c < 3; ++c) {
+        own[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (INTERIOR || T.in_img) own[c] = __ldg(reinterpret_cast<const float4*>(row + c * stride));
+        // the halo groups go straight to shared memory (LDGSTS): no registers held across the latency
+        if (T.halo) us_cp_async16(xs_row + c * US_XW + T.halo_soff, row + c * stride + T.halo_goff);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        if (INTERIOR || T.in_img) *reinterpret_cast<float4*>(xs_row + c * US_XW + 4 + 4 * T.lane) = own[c];
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncwarp();
+    if (!INTERIOR && T.rfl_dst >= 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xs_row[c * US_XW + T.rfl_dst] = xs_row[c * US_XW + T.rfl_src];
+    }
+    if (!INTERIOR) __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* xrow = xs_row + c * US_XW;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (INTERIOR || T.lane_fast) {
             const float4 lft = *reinterpret_cast<const float4*>(xrow + 4 * T.lane);
             const float4 rgt = *reinterpret_cast<const float4*>(xrow + 8 + 4 * T.lane);
-            const float t[12] = {lft.x, lft.y, lft.z, lft.w, own.x, own.y, own.z, own.w, rgt.x, rgt.y, rgt.z, rgt.w};
+            const float t[12] = {lft.x, lft.y, lft.z, lft.w, own[c].x, own[c].y, own[c].z, own[c].w, rgt.x, rgt.y, rgt.z, rgt.w};
             o.x = row9(t + 0, true); o.y = row9(t + 1, true); o.z = row9(t + 2, true); o.w = row9(t + 3, true);
-        } else {
+        } else if (T.in_img) {
+            // partial groups at the right image edge and the scalar-tail elements: per pixel, taps from the staged row
             float r[4] = {0.f, 0.f, 0.f, 0.f};
-            const float* __restrict__ row0 = row - T.gx0;
 #pragma unroll 1
             for (int i = 0; i < 4; ++i) {
                 const int gx = T.gx0 + i;
-                if (gx < 0 || gx >= T.w) continue;
-                if (T.w == 1) { r[i] = __ldg(row0); continue; }      // GaussianBlur shrinks the kernel to [1] on a 1-pixel axis
+                if (gx >= T.w) continue;
+                if (T.w == 1) { r[i] = xrow[4 + 4 * T.lane + i]; continue; }      // GaussianBlur shrinks the kernel to [1] on a 1-pixel axis
                 float t[9];
 #pragma unroll
-                for (int j = 0; j < 9; ++j) t[j] = __ldg(row0 + reflect101(gx - 4 + j, T.w));
+                for (int j = 0; j < 9; ++j) t[j] = xrow[4 * T.lane + i + j];
                 r[i] = row9(t, 3 * gx + c < T.tail_from);
             }
             o = make_float4(r[0], r[1], r[2], r[3]);
@@ -306,8 +327,16 @@ k_unsharp_strip(const float* __restrict__ lap, int w, int h, int pitch, size_t s
     T.tail_from = 3 * w - (3 * w) % 8;       // first interleaved element handled by the scalar filter loops
     T.gx0 = T.x0 - 4 + 4 * T.lane;           // this lane's 4 computed columns
     T.in_img = T.gx0 >= 0 && T.gx0 < w;
-    // all 12 taps of the lane's 4 pixels inside the image, none of them in the scalar-tail region
-    T.lane_fast = T.gx0 - 4 >= 0 && T.gx0 + 7 <= w - 1 && 3 * (T.gx0 + 3) + 2 < T.tail_from && w > 1;
+    // the lane's 4 pixels inside the image, none of them in the scalar-tail region (taps outside the image are
+    // mirrored into the staged row, see us_row_pass)
+    T.lane_fast = T.gx0 >= 0 && T.gx0 + 3 <= w - 1 && 3 * (T.gx0 + 3) + 2 < T.tail_from && w > 1;
+    // staged slot k of a row holds column x0 - 8 + k; lanes 0-7 mirror columns -8..-1, lanes 8-15 columns w..w+7
+    T.rfl_dst = T.rfl_src = -1;
+    if (T.lane < 8 && T.x0 == 0 && w > 1) { T.rfl_dst = T.lane; T.rfl_src = reflect101(T.lane - 8, w) + 8; }
+    if (T.lane >= 8 && T.lane < 16 && w > 1) {
+        const int col = w + T.lane - 8;
+        if (col <= T.x0 + 127 && col >= T.x0 - 8) { T.rfl_dst = col - T.x0 + 8; T.rfl_src = reflect101(col, w) - T.x0 + 8; }
+    }
     T.halo = (T.lane == 0 && T.x0 - 8 >= 0) || (T.lane == 1 && T.x0 + 124 < w);
     T.halo_goff = T.lane == 0 ? -4 : 124;    // lane 0: columns x0-8.. (gx0 = x0-4); lane 1: columns x0+124.. (gx0 = x0)
     T.halo_soff = T.lane == 0 ? 0 : US_XW - 4;
