@@ -39,15 +39,17 @@ void make_uniq(const std::vector<Point2f>& pts, std::vector<Point2f>& out, std::
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-DelaunayMesh::DelaunayMesh(int width, int height) {
+DelaunayMesh::DelaunayMesh(int width, int height, int expected_points) {
     const float big = 3.f * (float)(width > height ? width : height);
     top_left_ = {0.f, 0.f};
     bottom_right_ = {(float)width, (float)height};
+    q_.reserve((size_t)3 * (expected_points > 0 ? expected_points : 64) + 16);
+    org_.reserve(2 * q_.capacity());
+    pt_.reserve((size_t)(expected_points > 0 ? expected_points : 64) + 8);
     // slot 0 of both tables is the null element
-    next_.assign(4, 0);
-    org_.assign(4, 0);
+    q_.push_back(Quad{});
+    org_.assign(2, 0);
     pt_.push_back({0.f, 0.f});
-    first_edge_.push_back(0);
     const int a = new_vertex({big, 0.f}), b = new_vertex({0.f, big}), c = new_vertex({-big, -big});
     const int ab = new_quad(), bc = new_quad(), ca = new_quad();
     set_ends(ab, a, b);
@@ -61,14 +63,16 @@ DelaunayMesh::DelaunayMesh(int width, int height) {
 
 int DelaunayMesh::new_quad() {
     if (free_quad_ <= 0) {
-        next_.insert(next_.end(), 4, 0);
-        org_.insert(org_.end(), 4, 0);
-        free_quad_ = (int)(next_.size() / 4) - 1;
+        q_.push_back(Quad{});
+        org_.insert(org_.end(), 2, 0);
+        free_quad_ = (int)q_.size() - 1;
     }
     const int e = free_quad_ * 4;
-    free_quad_ = next_[e + 1];
-    next_[e] = e; next_[e + 1] = e + 3; next_[e + 2] = e + 2; next_[e + 3] = e + 1;
-    org_[e] = org_[e + 1] = org_[e + 2] = org_[e + 3] = 0;
+    Quad& q = q_[free_quad_];
+    free_quad_ = q.next[1];
+    q.next[0] = e; q.next[1] = e + 3; q.next[2] = e + 2; q.next[3] = e + 1;
+    org_[e >> 1] = org_[(e >> 1) + 1] = 0;
+    q.opt[0] = q.opt[1] = pt_[0];
     return e;
 }
 
@@ -76,32 +80,33 @@ void DelaunayMesh::free_quad_of(int e) {
     splice(e, oprev(e));
     const int s = sym(e);
     splice(s, oprev(s));
-    const int q = e >> 2;
-    next_[4 * q] = 0;
-    next_[4 * q + 1] = free_quad_;
-    free_quad_ = q;
+    Quad& q = q_[e >> 2];
+    q.next[0] = 0;
+    q.next[1] = free_quad_;
+    free_quad_ = e >> 2;
 }
 
 int DelaunayMesh::new_vertex(Point2f p) {
     pt_.push_back(p);
-    first_edge_.push_back(0);
     return (int)pt_.size() - 1;
 }
 
 void DelaunayMesh::splice(int a, int b) {
-    int& an = next_[a];
-    int& bn = next_[b];
-    int& arn = next_[rot(an, 1)];
-    int& brn = next_[rot(bn, 1)];
+    int& an = next_of(a);
+    int& bn = next_of(b);
+    int& arn = next_of(rot(an, 1));
+    int& brn = next_of(rot(bn, 1));
     std::swap(an, bn);
     std::swap(arn, brn);
 }
 
 void DelaunayMesh::set_ends(int e, int o, int d) {
-    org_[e] = o;
-    org_[sym(e)] = d;
-    first_edge_[o] = e;
-    first_edge_[d] = sym(e);
+    Quad& q = q_[e >> 2];
+    const int r = e & 3;                    // primal: 0 or 2
+    org_[e >> 1] = o;
+    org_[(e >> 1) ^ 1] = d;
+    q.opt[r >> 1] = pt_[o];
+    q.opt[(r >> 1) ^ 1] = pt_[d];
 }
 
 int DelaunayMesh::connect(int a, int b) {
@@ -137,37 +142,71 @@ int in_circle(Point2f pt, Point2f a, Point2f b, Point2f c) {
 }  // namespace
 
 int DelaunayMesh::side_of(Point2f p, int e) const {
-    const double cw = tri_area(p, pt_[dst(e)], pt_[org(e)]);
+    const Quad& q = q_[e >> 2];
+    const int k = (e >> 1) & 1;
+    const double cw = tri_area(p, q.opt[k ^ 1], q.opt[k]);
     return (cw > 0) - (cw < 0);
 }
 
-DelaunayMesh::Where DelaunayMesh::locate(Point2f p, int& out_edge, int& out_vertex) {
+bool DelaunayMesh::begin_walk(Point2f p, Walk& w) const {
+    w.p = p;
+    w.e = 0;
+    w.r_cur = 0;
+    w.budget = (int)q_.size() * 4;
+    w.where = kOutside;
+    if (p.x < top_left_.x || p.y < top_left_.y || p.x >= bottom_right_.x || p.y >= bottom_right_.y) return false;
+    w.where = kError;
+    w.e = recent_;
+    w.r_cur = side_of(p, w.e);
+    if (w.r_cur > 0) { w.e = sym(w.e); w.r_cur = -w.r_cur; }
+    return true;
+}
+
+bool DelaunayMesh::walk_step(Walk& w) const {
+    if (w.budget-- <= 0) return false;                 // Subdiv2D::locate gives up after 4 * quads steps
+    const Quad* __restrict__ q = q_.data();
+    const Point2f p = w.p;
+    const int e = w.e;
+    const Quad& qe = q[e >> 2];
+    const int on = qe.next[e & 3], dp = rot(qe.next[(e + 3) & 3], 3);
+    const Quad& qon = q[on >> 2];
+    const Quad& qdp = q[dp >> 2];
+    const int kon = (on >> 1) & 1, kdp = (dp >> 1) & 1;
+    const double a_on = tri_area(p, qon.opt[kon ^ 1], qon.opt[kon]), a_dp = tri_area(p, qdp.opt[kdp ^ 1], qdp.opt[kdp]);
+    if (w.r_cur != 0 && a_on != 0 && a_dp != 0) {
+        // general position (the common case): the four sign combinations of Subdiv2D::locate collapse to
+        // "inside" or one conditional move, so the walk has no data-dependent branch to mispredict
+        if (a_on > 0 && a_dp > 0) { w.where = kInside; return false; }
+        const int go_dp = -(int)(a_on > 0);          // right of onext (then not right of dprev): cross dprev, else onext
+        w.e = on ^ ((on ^ dp) & go_dp);
+        w.r_cur = -1;
+        return true;
+    }
+    const int r_on = (a_on > 0) - (a_on < 0), r_dp = (a_dp > 0) - (a_dp < 0);
+    if (r_dp > 0) {
+        if (r_on > 0 || (r_on == 0 && w.r_cur == 0)) { w.where = kInside; return false; }
+        w.r_cur = r_on;
+        w.e = on;
+    } else if (r_on > 0) {
+        if (r_dp == 0 && w.r_cur == 0) { w.where = kInside; return false; }
+        w.r_cur = r_dp;
+        w.e = dp;
+    } else if (w.r_cur == 0 && side_of(pt_[dst(on)], e) >= 0) {
+        w.e = sym(e);
+    } else {
+        w.r_cur = r_on;
+        w.e = on;
+    }
+    return true;
+}
+
+DelaunayMesh::Where DelaunayMesh::classify(const Walk& w, int& out_edge, int& out_vertex) {
     out_edge = 0;
     out_vertex = 0;
-    if (p.x < top_left_.x || p.y < top_left_.y || p.x >= bottom_right_.x || p.y >= bottom_right_.y) return kOutside;
-    const int budget = (int)next_.size();
-    int e = recent_;
-    int r_cur = side_of(p, e);
-    if (r_cur > 0) { e = sym(e); r_cur = -r_cur; }
-    Where where = kError;
-    for (int i = 0; i < budget; ++i) {
-        const int on = onext(e), dp = dprev(e);
-        const int r_on = side_of(p, on), r_dp = side_of(p, dp);
-        if (r_dp > 0) {
-            if (r_on > 0 || (r_on == 0 && r_cur == 0)) { where = kInside; break; }
-            r_cur = r_on;
-            e = on;
-        } else if (r_on > 0) {
-            if (r_dp == 0 && r_cur == 0) { where = kInside; break; }
-            r_cur = r_dp;
-            e = dp;
-        } else if (r_cur == 0 && side_of(pt_[dst(on)], e) >= 0) {
-            e = sym(e);
-        } else {
-            r_cur = r_on;
-            e = on;
-        }
-    }
+    if (w.where == kOutside) return kOutside;
+    const int e = w.e;
+    const Point2f p = w.p;
+    Where where = w.where;
     recent_ = e;
     if (where == kInside) {
         const Point2f o = pt_[org(e)], d = pt_[dst(e)];
@@ -187,8 +226,16 @@ DelaunayMesh::Where DelaunayMesh::locate(Point2f p, int& out_edge, int& out_vert
 }
 
 int DelaunayMesh::insert(Point2f p) {
+    Walk w;
+    if (begin_walk(p, w))
+        while (walk_step(w)) {}
+    return finish_insert(w);
+}
+
+int DelaunayMesh::finish_insert(Walk& w) {
+    const Point2f p = w.p;
     int cur = 0, vtx = 0;
-    const Where where = locate(p, cur, vtx);
+    const Where where = classify(w, cur, vtx);
     if (where == kOutside) { err_ = "point outside the subdivision rectangle (cv::Subdiv2D: StsOutOfRange)"; return -1; }
     if (where == kError) { err_ = "point location failed (cv::Subdiv2D: StsBadSize)"; return -1; }
     if (where == kVertex) return vtx;
@@ -207,7 +254,7 @@ int DelaunayMesh::insert(Point2f p) {
         cur = oprev(base);
     } while (dst(cur) != first);
     cur = oprev(base);
-    const int budget = (int)next_.size();
+    const int budget = (int)q_.size() * 4;
     for (int i = 0; i < budget; ++i) {
         const int t = oprev(cur);
         const int t_dst = dst(t), c_org = org(cur), c_dst = dst(cur);
@@ -225,7 +272,7 @@ int DelaunayMesh::insert(Point2f p) {
 
 void DelaunayMesh::triangles(std::vector<int32_t>& ids) const {
     ids.clear();
-    const int total = (int)next_.size();
+    const int total = (int)q_.size() * 4;
     std::vector<char> seen(total, 0);
     for (int e = 4; e < total; e += 2) {
         if (seen[e]) continue;
@@ -242,6 +289,103 @@ void DelaunayMesh::triangles(std::vector<int32_t>& ids) const {
     }
 }
 
+namespace {
+
+// One frame of a batch: its deduplicated points, its mesh and the walk of the point being inserted.
+struct BatchJob {
+    std::vector<Point2f> uniq;
+    std::vector<int32_t> first, owner;
+    DelaunayMesh* mesh = nullptr;
+    DelaunayMesh::Walk walk;
+    size_t next = 0;            // next point of `uniq` to insert
+    int slot = -1;              // index of the point set this job triangulates
+    bool alive = false, failed = false;
+    ~BatchJob() { delete mesh; }
+
+    void open(const std::vector<Point2f>& points, int index, int width, int height) {
+        std::vector<Point2f> clipped = points;
+        clip_points(clipped, width, height);
+        uniq.clear();
+        first.clear();
+        make_uniq(clipped, uniq, &first);
+        owner.assign(4, -1);
+        delete mesh;
+        mesh = new DelaunayMesh(width, height, (int)uniq.size());
+        next = 0;
+        slot = index;
+        failed = false;
+        alive = true;
+        start_next();
+    }
+    // begins the walk of the next point; alive = false when the set is exhausted or an insertion failed
+    void start_next() {
+        while (next < uniq.size()) {
+            if (mesh->begin_walk(uniq[next], walk)) return;
+            complete();                      // outside the rectangle: finish_insert reports it
+            if (!alive) return;
+        }
+        alive = false;
+    }
+    // the walk of point `next` has ended: update the topology
+    void complete() {
+        const int v = mesh->finish_insert(walk);
+        if (v < 0) { failed = true; alive = false; return; }
+        if (v >= (int)owner.size()) owner.resize(v + 1, -1);
+        if (owner[v] < 0) owner[v] = first[next];
+        ++next;
+    }
+    void close(std::vector<int32_t>& tri_idx, bool& ok, std::string& error) {
+        tri_idx.clear();
+        ok = !failed;
+        if (failed) { error = mesh->error(); return; }
+        std::vector<int32_t> ids;
+        mesh->triangles(ids);
+        tri_idx.resize(ids.size());
+        for (size_t i = 0; i < ids.size(); ++i) tri_idx[i] = owner[ids[i]];
+    }
+};
+
+template <int K>
+void run_batch(const std::vector<Point2f>* sets, int count, int width, int height, std::vector<int32_t>* tri_idx, bool* ok,
+               std::string* errors) {
+    BatchJob jobs[K];
+    int issued = 0, open_jobs = 0;
+    for (int k = 0; k < K && issued < count; ++k, ++issued, ++open_jobs) jobs[k].open(sets[issued], issued, width, height);
+    while (open_jobs > 0) {
+        // one walk step of every mesh per round: K independent dependency chains in flight
+#pragma GCC unroll 8
+        for (int k = 0; k < K; ++k) {
+            BatchJob& j = jobs[k];
+            if (j.slot < 0) continue;
+            if (j.alive && j.mesh->walk_step(j.walk)) continue;
+            if (j.alive) {
+                j.complete();
+                if (j.alive) j.start_next();
+                if (j.alive) continue;
+            }
+            j.close(tri_idx[j.slot], ok[j.slot], errors[j.slot]);
+            j.slot = -1;
+            --open_jobs;
+            if (issued < count) {
+                j.open(sets[issued], issued, width, height);
+                ++issued;
+                ++open_jobs;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+void triangulate_points_batch(const std::vector<Point2f>* sets, int count, int width, int height,
+                              std::vector<int32_t>* tri_idx, bool* ok, std::string* errors, int ways) {
+    if (ways >= 8) run_batch<8>(sets, count, width, height, tri_idx, ok, errors);
+    else if (ways >= 6) run_batch<6>(sets, count, width, height, tri_idx, ok, errors);
+    else if (ways >= 4) run_batch<4>(sets, count, width, height, tri_idx, ok, errors);
+    else if (ways >= 2) run_batch<2>(sets, count, width, height, tri_idx, ok, errors);
+    else run_batch<1>(sets, count, width, height, tri_idx, ok, errors);
+}
+
 bool triangulate_points(std::vector<Point2f> points, int width, int height, std::vector<int32_t>& tri_idx,
                         std::string* error) {
     tri_idx.clear();
@@ -249,7 +393,7 @@ bool triangulate_points(std::vector<Point2f> points, int width, int height, std:
     std::vector<Point2f> uniq;
     std::vector<int32_t> first;
     make_uniq(points, uniq, &first);
-    DelaunayMesh mesh(width, height);
+    DelaunayMesh mesh(width, height, (int)uniq.size());
     std::vector<int32_t> owner(4, -1);        // mesh vertex id -> index of its first occurrence in `points`
     for (size_t i = 0; i < uniq.size(); ++i) {
         const int v = mesh.insert(uniq[i]);

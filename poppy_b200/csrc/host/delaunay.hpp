@@ -29,11 +29,30 @@ void make_uniq(const std::vector<Point2f>& pts, std::vector<Point2f>& out, std::
 class DelaunayMesh {
 public:
     // bounding rect [0,w) x [0,h), as Subdiv2D(Rect(0,0,w,h))
-    DelaunayMesh(int width, int height);
+    // expected_points: capacity hint (the tables never move while points are inserted when it is large enough)
+    DelaunayMesh(int width, int height, int expected_points = 0);
 
     // Subdiv2D::insert. Returns the vertex id (>= 4 for real points) or -1 when the point is outside the rect
     // (where cv::Subdiv2D throws StsOutOfRange); error() then describes it.
     int insert(Point2f pt);
+
+    enum Where { kError = -2, kOutside = -1, kInside = 0, kVertex = 1, kOnEdge = 2 };
+    struct Walk {
+        Point2f p;
+        int e, r_cur, budget;
+        Where where;
+    };
+
+    // The same insertion cut at the boundaries of its point-location walk, so that a caller can advance the walks of
+    // several independent meshes in one instruction stream (triangulate_points_batch): the walk is a chain of dependent
+    // loads and compares (~100 cycles per step, ~120 steps per point at 20k points) that leaves the core idle; the
+    // out-of-order window overlaps the chains of different meshes.
+    //   begin_walk(p, w)   false: p is outside the rectangle (w.where = kOutside)
+    //   walk_step(w)       one step of Subdiv2D::locate; false when the walk has ended
+    //   finish_insert(w)   classification of the final edge + the topology update; returns what insert() returns
+    bool begin_walk(Point2f pt, Walk& w) const;
+    bool walk_step(Walk& w) const;
+    int finish_insert(Walk& w);
 
     // Subdiv2D::getTriangleList order; each triangle as three vertex ids (all >= 4).
     void triangles(std::vector<int32_t>& vertex_ids) const;
@@ -43,16 +62,25 @@ public:
     const std::string& error() const { return err_; }
 
 private:
+    // One quad-edge record = half a cache line: the four onext links and a copy of the origin coordinates of the two
+    // primal edges, so that the point-location walk (latency-bound pointer chasing, ~120 steps per inserted point at
+    // 20k points; three records per step: the current edge's, its onext's and its dprev's) never chases vertex
+    // indices and its working set (32 B x 3 quads per point) stays inside a 2 MB L2. Vertex ids live in a cold table.
+    struct alignas(32) Quad {
+        int next[4];
+        Point2f opt[2];     // coordinates of org(4q) and org(4q + 2)
+    };
     // edge id = 4 * quad + rot
-    int onext(int e) const { return next_[e]; }
+    int& next_of(int e) { return q_[e >> 2].next[e & 3]; }
+    int onext(int e) const { return q_[e >> 2].next[e & 3]; }
     static int rot(int e, int r) { return (e & ~3) + ((e + r) & 3); }
     static int sym(int e) { return e ^ 2; }
-    int oprev(int e) const { return rot(next_[rot(e, 1)], 1); }
-    int lnext(int e) const { return rot(next_[rot(e, 3)], 1); }
-    int lprev(int e) const { return sym(next_[e]); }
-    int dprev(int e) const { return rot(next_[rot(e, 3)], 3); }
-    int org(int e) const { return org_[e]; }
-    int dst(int e) const { return org_[sym(e)]; }
+    int oprev(int e) const { return rot(onext(rot(e, 1)), 1); }
+    int lnext(int e) const { return rot(onext(rot(e, 3)), 1); }
+    int lprev(int e) const { return sym(onext(e)); }
+    int dprev(int e) const { return rot(onext(rot(e, 3)), 3); }
+    int org(int e) const { return org_[e >> 1]; }          // primal edges only (e even)
+    int dst(int e) const { return org_[(e >> 1) ^ 1]; }
 
     int new_quad();
     void free_quad_of(int e);
@@ -61,14 +89,12 @@ private:
     void set_ends(int e, int o, int d);
     int connect(int a, int b);
     void flip(int e);
-    int side_of(Point2f p, int e) const;      // sign of "p is right of e"
-    enum Where { kError = -2, kOutside = -1, kInside = 0, kVertex = 1, kOnEdge = 2 };
-    Where locate(Point2f p, int& edge, int& vertex);
+    int side_of(Point2f p, int e) const;      // sign of "p is right of e" (primal edges only)
+    Where classify(const Walk& w, int& edge, int& vertex);
 
-    std::vector<int> next_;     // 4 per quad-edge
-    std::vector<int> org_;      // 4 per quad-edge (origin vertex of each of the 4 directed edges; odd slots unused)
+    std::vector<Quad> q_;
+    std::vector<int> org_;      // 2 per quad: origin vertex of edges 4q and 4q + 2
     std::vector<Point2f> pt_;
-    std::vector<int> first_edge_;
     int free_quad_ = 0;
     int recent_ = 0;
     Point2f top_left_{0, 0}, bottom_right_{0, 0};
@@ -80,5 +106,10 @@ private:
 // Returns false (with `error`) where the reference would throw.
 bool triangulate_points(std::vector<Point2f> points, int width, int height, std::vector<int32_t>& tri_idx,
                         std::string* error = nullptr);
+
+// The same for `count` independent point sets (the frames of a sequence) on one thread, with the point-location walks
+// of up to `ways` meshes interleaved (see DelaunayMesh::walk_step). ok[i] / errors[i] as triangulate_points.
+void triangulate_points_batch(const std::vector<Point2f>* sets, int count, int width, int height,
+                              std::vector<int32_t>* tri_idx, bool* ok, std::string* errors, int ways = 4);
 
 }  // namespace poppy

@@ -1,7 +1,9 @@
 // extern "C" layer of the host stages (include/poppy_host.h).
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -105,12 +107,21 @@ int poppy_host_plan_create(poppy_host_plan** out, const float* p1, const float* 
     std::atomic<int> next{0}, failed{-1};
     int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
     nt = std::max(1, std::min(nt, n_frames));
+    // POPPY_PLAN_WAYS > 1: a thread triangulates that many frames at once with their point-location walks interleaved
+    // (pays where the quad-edge tables of several meshes fit the core's cache; see delaunay.hpp)
+    const char* ways_env = std::getenv("POPPY_PLAN_WAYS");
+    const int ways = ways_env ? std::max(1, std::min(8, std::atoi(ways_env))) : 1;
     auto work = [&] {
-        for (int f; (f = next.fetch_add(1)) < n_frames;)
-            if (!poppy::triangulate_points(plan->points[f], w, h, tris[f], &errs[f])) {
-                int expected = -1;
-                failed.compare_exchange_strong(expected, f);
-            }
+        std::unique_ptr<bool[]> ok(new bool[ways]);
+        for (int f0; (f0 = next.fetch_add(ways)) < n_frames;) {
+            const int cnt = std::min(ways, n_frames - f0);
+            poppy::triangulate_points_batch(&plan->points[f0], cnt, w, h, &tris[f0], ok.get(), &errs[f0], ways);
+            for (int i = 0; i < cnt; ++i)
+                if (!ok[i]) {
+                    int expected = -1;
+                    failed.compare_exchange_strong(expected, f0 + i);
+                }
+        }
     };
     std::vector<std::thread> pool;
     for (int i = 1; i < nt; ++i) pool.emplace_back(work);
