@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpoppy_cuda.so")
+LIB_PATH = os.environ.get("POPPY_CUDA_LIB") or os.path.join(_HERE, "libpoppy_cuda.so")   # override: A/B builds only
 
 _lib = None
 

@@ -27,10 +27,11 @@ void launch_bgr_to_bgrx(cudaStream_t st, const uint8_t* bgr, uchar4* out, int w,
 void launch_mask_basis(cudaStream_t st, const float* gabor_bgr, float* m2, int bpitch, int w, int h);
 // paint_triangles + create_map + remap for both images, one CTA per 64x32 screen tile (reference src/algo.cpp:95-106,
 // 146-176, 232-238). warped: per frame two planes of packed BGRX words (remap of image 1, of image 2), rows `wpitch`
-// words apart, `wstride` words per plane; tri_map_out (nullable) receives frame 0's ID map
+// words apart, `wstride` words per plane; tri_map_out (nullable) receives frame 0's ID map. src1/src2: point-sampled,
+// border-addressed (zero) uchar4 BGRX textures over cudaArrayTextureGather arrays, unnormalised coordinates
 void launch_raster_warp(cudaStream_t st, const TriRaster* rast, const TriInverse* inv, const FrameParams* fp, int max_tri,
-                        const int* tile_off, const int* tile_list, int cap, const int* overflow, const uchar4* src1,
-                        const uchar4* src2, uint32_t* warped, int wpitch, size_t wstride, int* tri_map_out, int w, int h,
+                        const int* tile_off, const int* tile_list, int cap, const int* overflow,
+                        cudaTextureObject_t src1, cudaTextureObject_t src2, uint32_t* warped, int wpitch, size_t wstride, int* tri_map_out, int w, int h,
                         int frames);
 
 // ---- kernels_pyramid.cu ------------------------------------------------------------------------------------------

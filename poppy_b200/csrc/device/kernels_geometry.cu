@@ -195,7 +195,7 @@ __global__ void k_tri_geometry(const int3* __restrict__ tri_idx, const FramePara
     TriInverse out;
     inv3(M1, out.a);
     inv3(M2, out.b);
-    out.pad[0] = out.pad[1] = 0.f;
+    out.pad_a[0] = out.pad_a[1] = out.pad_a[2] = out.pad_b[0] = out.pad_b[1] = out.pad_b[2] = 0.f;
     inv_out[(size_t)f * max_tri + t] = out;
 }
 

@@ -373,7 +373,7 @@ __device__ __forceinline__ void down0_body_mask(const float* __restrict__ basis,
 // full with cp.async.bulk (the 1-D form of TMA: one instruction per 1056-byte row segment, completion signalled on an
 // mbarrier), so ~8 KB per warp are in flight without holding a single register, and the walk itself only issues
 // shared-memory loads. A ring is private to its warp: the only synchronisation is the stage's mbarrier (data landed)
-// and a __syncwarp() before a consumed stage is refilled.
+// and a __syncwarp() + fence.proxy.async before a consumed stage is refilled.
 constexpr int D0_NS = 8;                   // ring depth in source rows
 constexpr int D0_SEG = 264;                // elements per staged segment: source columns 2*X0 - 4 .. 2*X0 + 259
 constexpr int D0_ROWS = 2 * DN_R + 3;      // source rows 2*y0 - 2 .. 2*y0 + 2*DN_R of one walk
@@ -441,6 +441,10 @@ struct Down0Feed {
     // rows r0 .. r0 + n - 1 have been consumed by every lane: refill their stages with the rows D0_NS further down
     __device__ __forceinline__ void refill(int r0, int n) const {
         __syncwarp();
+        // The stage was read through the generic proxy and is about to be written through the async proxy (TMA): without
+        // this cross-proxy fence the refill can overtake the reads (seen on B200 as rare +-1 LSB differences in the first
+        // frames of a chunk when two render lanes overlap; tools/stress_determinism.py).
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         if (lane == 0) {
             for (int r = r0 + D0_NS; r < r0 + n + D0_NS; ++r)
                 if (r < D0_ROWS) issue(r);

@@ -53,7 +53,11 @@ struct poppy_cuda_ctx {
     size_t g_floats = 0, o_floats = 0;   // per chunk
 
     // resident
-    uchar4 *d_src1 = nullptr, *d_src2 = nullptr, *d_src_chain = nullptr;
+    uchar4* d_src_stage = nullptr;       // linear BGRX staging for the array uploads
+    // sources as uchar4 CUDA arrays (texture gather) + point/border texture objects; index 2 = the chain source
+    // (frame j-1 of a recurrence, reference src/poppy.hpp:178-179)
+    cudaArray_t a_src[3] = {nullptr, nullptr, nullptr};
+    cudaTextureObject_t t_src[3] = {0, 0, 0};
     float* d_mbasis = nullptr;
     float2 *d_pts1_raw = nullptr, *d_pts2_raw = nullptr, *d_pts1 = nullptr, *d_pts2 = nullptr, *d_morphed = nullptr;
     uint8_t* d_frames = nullptr;
@@ -233,7 +237,7 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
 
     const bool chained = chain && first > 0;
     const float2* p1 = chained ? c->d_morphed + (size_t)(first - 1) * c->max_points : c->d_pts1;
-    const uchar4* src1 = chained ? c->d_src_chain : c->d_src1;
+    const cudaTextureObject_t src1 = chained ? c->t_src[2] : c->t_src[0];
     float2* morphed = c->d_morphed + (size_t)first * c->max_points;
     const int n = c->n_points, w = c->w, h = c->h, L = c->levels;
 
@@ -252,7 +256,7 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
     }
     {   Scope s(c, KC_WARP, st);
         launch_raster_warp(st, ln.d_rast, ln.d_inv, ln.d_fp, c->max_tri, ln.d_tile_off, ln.d_tile_list, c->list_cap,
-                           ln.d_overflow, src1, c->d_src2, ln.d_warped, c->pitch0(), c->padded_pixels(),
+                           ln.d_overflow, src1, c->t_src[1], ln.d_warped, c->pitch0(), c->padded_pixels(),
                            c->keep_stages ? ln.d_trimap : nullptr,
                            w, h, nb);
     }
@@ -280,7 +284,9 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
     }
     if (chain) {
         Scope s(c, KC_MISC, st);
-        launch_bgr_to_bgrx(st, c->d_frames + (size_t)(first + nb - 1) * c->frame_bytes(), c->d_src_chain, w, h);
+        launch_bgr_to_bgrx(st, c->d_frames + (size_t)(first + nb - 1) * c->frame_bytes(), c->d_src_stage, w, h);
+        CU_TRY(c, cudaMemcpy2DToArrayAsync(c->a_src[2], 0, 0, c->d_src_stage, (size_t)w * 4, (size_t)w * 4, h,
+                                           cudaMemcpyDeviceToDevice, st));
     }
     CU_TRY(c, cudaGetLastError());
     return 0;
@@ -352,9 +358,20 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
         c->list_cap = (int)std::min<long long>(all, want);
     }
     const size_t px = c->pixels();
-    CR_TRY(dmalloc(&c->d_src1, px));
-    CR_TRY(dmalloc(&c->d_src2, px));
-    CR_TRY(dmalloc(&c->d_src_chain, px));
+    CR_TRY(dmalloc(&c->d_src_stage, px));
+    for (int i = 0; i < 3; ++i) {
+        const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+        CR_TRY(cudaMallocArray(&c->a_src[i], &fmt, (size_t)width, (size_t)height, cudaArrayTextureGather));
+        cudaResourceDesc res{};
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = c->a_src[i];
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeBorder;      // BORDER_CONSTANT(0)
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        CR_TRY(cudaCreateTextureObject(&c->t_src[i], &res, &td, nullptr));
+    }
     CR_TRY(dmalloc(&c->d_mbasis, c->padded_pixels()));
     CR_TRY(dmalloc(&c->d_pts1_raw, (size_t)max_points));
     CR_TRY(dmalloc(&c->d_pts2_raw, (size_t)max_points));
@@ -376,7 +393,11 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
     collect_timing(c);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     free_chunk(c);
-    cudaFree(c->d_src1); cudaFree(c->d_src2); cudaFree(c->d_src_chain); cudaFree(c->d_mbasis);
+    cudaFree(c->d_src_stage); cudaFree(c->d_mbasis);
+    for (int i = 0; i < 3; ++i) {
+        if (c->t_src[i]) cudaDestroyTextureObject(c->t_src[i]);
+        if (c->a_src[i]) cudaFreeArray(c->a_src[i]);
+    }
     cudaFree(c->d_pts1_raw); cudaFree(c->d_pts2_raw); cudaFree(c->d_pts1); cudaFree(c->d_pts2); cudaFree(c->d_morphed);
     cudaFree(c->d_frames); cudaFree(c->d_sum);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -446,9 +467,12 @@ int poppy_cuda_set_pair(poppy_cuda_ctx* c, const uint8_t* bgr1, size_t step1, co
     int rc = 0;
     auto run = [&]() -> int {
         CU_TRY(c, cudaMemcpy2DAsync(stage, row, bgr1, step1, row, c->h, cudaMemcpyHostToDevice, c->stream));
-        launch_bgr_to_bgrx(c->stream, stage, c->d_src1, c->w, c->h);
+        const size_t trow = (size_t)c->w * 4;
+        launch_bgr_to_bgrx(c->stream, stage, c->d_src_stage, c->w, c->h);
+        CU_TRY(c, cudaMemcpy2DToArrayAsync(c->a_src[0], 0, 0, c->d_src_stage, trow, trow, c->h, cudaMemcpyDeviceToDevice, c->stream));
         CU_TRY(c, cudaMemcpy2DAsync(stage, row, bgr2, step2, row, c->h, cudaMemcpyHostToDevice, c->stream));
-        launch_bgr_to_bgrx(c->stream, stage, c->d_src2, c->w, c->h);
+        launch_bgr_to_bgrx(c->stream, stage, c->d_src_stage, c->w, c->h);
+        CU_TRY(c, cudaMemcpy2DToArrayAsync(c->a_src[1], 0, 0, c->d_src_stage, trow, trow, c->h, cudaMemcpyDeviceToDevice, c->stream));
         CU_TRY(c, cudaMemcpy2DAsync(gstage, grow, gabor, gstep, grow, c->h, cudaMemcpyHostToDevice, c->stream));
         launch_mask_basis(c->stream, gstage, c->d_mbasis, c->pitch0(), c->w, c->h);
         c->launches += 3; c->class_launches[KC_MISC] += 3;
