@@ -25,7 +25,8 @@ int main() {
     td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
     cudaTextureObject_t t; if (cudaCreateTextureObject(&t, &r, &td, nullptr) != cudaSuccess) { printf("texobj failed\n"); return 1; }
     // (X+1, Y+1) for X,Y = (0,0), (1,1), (-1,0), (3,2), (-2,0), (4,0), (2,-1)
-    float2 h_at[] = {{1, 1}, {2, 2}, {0, 1}, {4, 3}, {-1, 1}, {5, 1}, {3, 0}};
+    float2 h_at[] = {{1, 1}, {2, 2}, {0, 1}, {4, 3}, {-1, 1}, {5, 1}, {3, 0},
+                     {6.7108864e7f, 1}, {-6.7108864e7f, 1}, {1, 6.7108864e7f}, {1, -6.7108864e7f}, {1e30f, 1}, {-1e30f, -1e30f}, {2147483648.f, 1}, {65536.f, 1}, {-65536.f, 1}, {16777216.f, 16777216.f}};
     const int n = sizeof h_at / sizeof h_at[0];
     float2* d_at; uint4* d_out; cudaMalloc(&d_at, sizeof h_at); cudaMalloc(&d_out, n * sizeof(uint4));
     cudaMemcpy(d_at, h_at, sizeof h_at, cudaMemcpyHostToDevice);
