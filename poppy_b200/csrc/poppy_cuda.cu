@@ -62,8 +62,9 @@ struct poppy_cuda_ctx {
     float2 *d_pts1_raw = nullptr, *d_pts2_raw = nullptr, *d_pts1 = nullptr, *d_pts2 = nullptr, *d_morphed = nullptr;
     uint8_t* d_frames = nullptr;
     unsigned long long* d_sum = nullptr;
-    // Chunk scratch. Two lanes, each with its own stream and scratch: consecutive chunks of a direct-mode render go to
-    // alternating lanes, so the instruction-bound kernels of one chunk overlap the bandwidth-bound kernels of the other.
+    // Chunk scratch. Up to four lanes (default three), each with its own stream and scratch: consecutive chunks of a
+    // direct-mode render go round-robin to the lanes, so the issue-bound kernels of one chunk overlap the latency- and
+    // bandwidth-bound kernels of the others.
     struct Lane {
         cudaStream_t stream = nullptr;
         cudaEvent_t ev_staged = nullptr, ev_done = nullptr;
@@ -77,7 +78,8 @@ struct poppy_cuda_ctx {
         float *d_mask0 = nullptr, *d_g = nullptr, *d_o = nullptr;
         FrameParams* h_fp = nullptr;         // pinned staging
         int32_t* h_tri = nullptr;
-    } lane[2];
+    } lane[4];
+    int want_lanes = 3;                      // POPPY_CUDA_LANES (1..4)
     int n_lanes = 0;                         // lanes allocated (0 = none yet)
     int n_tiles = 0, list_cap = 0;
 
@@ -135,13 +137,13 @@ size_t per_frame_scratch_bytes(const poppy_cuda_ctx* c) {
 int ensure_chunk(poppy_cuda_ctx* c) {
     int want = c->keep_stages ? 1 : c->want_chunk;
     if (want <= 0) {
-        // default: keep a lane's scratch under ~6 GiB and give the small pyramid levels enough CTAs
+        // default: keep a lane's scratch under ~12 GiB and give the small pyramid levels enough CTAs
         size_t per = per_frame_scratch_bytes(c);
-        want = (int)std::min<size_t>(16, std::max<size_t>(1, (6ull << 30) / std::max<size_t>(per, 1)));
+        want = (int)std::min<size_t>(32, std::max<size_t>(1, (12ull << 30) / std::max<size_t>(per, 1)));
     }
     want = std::max(1, std::min(want, c->max_frames));
     // a second lane only pays when a render spans several chunks
-    const int lanes = (c->keep_stages || c->single_lane || want >= c->max_frames) ? 1 : 2;
+    const int lanes = (c->keep_stages || c->single_lane || want >= c->max_frames) ? 1 : c->want_lanes;
     if (c->chunk == want && c->n_lanes == lanes) return 0;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     for (auto& l : c->lane) if (l.stream) CU_TRY(c, cudaStreamSynchronize(l.stream));
@@ -322,6 +324,7 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
     c->device = device; c->w = width; c->h = height; c->levels = pyramid_levels;
     c->max_points = max_points; c->max_tri = max_triangles; c->max_frames = max_batch_frames;
     if (const char* e = std::getenv("POPPY_CUDA_SINGLE_LANE")) c->single_lane = e[0] == '1';   // A/B switch for profiling
+    if (const char* e = std::getenv("POPPY_CUDA_LANES")) c->want_lanes = std::max(1, std::min(4, std::atoi(e)));
     auto bail = [&](int rc) { g_create_error = c->err; poppy_cuda_destroy(c); return rc; };
 #define CR_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
         fail(c, POPPY_CUDA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(POPPY_CUDA_ERR_CUDA); } } while (0)
