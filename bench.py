@@ -47,6 +47,60 @@ def algorithmic_bytes_per_frame(w: int, h: int, levels: int) -> int:
     return 23 * px[0] + 132 * sum(px[1:levels]) + 104 * px[levels]
 
 
+def ncu_traffic():
+    """DRAM bytes per frame of every kernel class from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py traffic): dram__bytes_read.sum + dram__bytes_write.sum."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return None
+
+
+def dominant_kernel_roofline(kern, W, H, F, chunk_frames, peak, traffic, levels=6):
+    """roofline of the kernel class with the largest share of the step, per launch: algorithmic bytes of that stage
+     / its CUDA-event launch time measured in this run."""
+    if not kern:
+        return None
+    P, lw, lh = [], W, H
+    for _ in range(levels + 1):
+        P.append(lw * lh)
+        lw, lh = (lw + 1) // 2, (lh + 1) // 2
+    px, mid = P[0], sum(P[1:levels])
+    # compulsory bytes per frame of each kernel class as designed: every input read once, every output written once
+    # (DESIGN.md section 5)
+    alg = {
+        "raster_warp": 8 * px + 8 * px / max(chunk_frames, 1),     # warped pair written; both sources read once per chunk
+        "unsharp_store": 15 * px,                                   # lapBlend 32FC3 read, 8UC3 frame written
+        # level 0: warped pair 8 + mask 4 + coarse (24 + 12)/4 read, out 12 written; level k: 28 + 9 read, 12 written;
+        # coarsest: 28 read, 12 written
+        "blend_collapse": 33 * px + 49 * mid + 40 * P[levels],
+        # level 0->1: warped 8 + basis 4 read, mask0 4 + 7 planes/4 written; level k->k+1: 28 read, 7 written
+        "pyr_down": 23 * px + 35 * mid,
+    }
+    k = kern[0]
+    name = k["kernel"]
+    per_chunk = {"raster_warp": 1, "unsharp_store": 1, "blend_collapse": levels + 1, "pyr_down": levels}
+    frames_per_launch = F * per_chunk[name] / k["launches_per_step"] if name in per_chunk else None
+    if name in ("blend_collapse", "pyr_down") and frames_per_launch:
+        # the class is a sequence of per-level launches: rate it over the whole sequence of one chunk
+        k = dict(k, us_per_launch=k["us_per_launch"] * per_chunk[name])
+        out_note = f"{per_chunk[name]} per-level launches of one chunk rated together"
+    else:
+        out_note = None
+    out = {"kernel": name, "us_per_launch": k["us_per_launch"], "share_of_step": k["share"]}
+    if out_note:
+        out["note"] = out_note
+    if name in alg and frames_per_launch:
+        b = alg[name] * frames_per_launch
+        ach = b / (k["us_per_launch"] * 1e-6) / 1e9
+        out.update({"algorithmic_bytes_per_launch": int(b), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak})
+    if traffic and name in traffic.get("bytes_per_frame", {}) and frames_per_launch:
+        out["traffic"] = int(traffic["bytes_per_frame"][name] * frames_per_launch)
+        out["traffic_source"] = traffic.get("source")
+    return out
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -148,6 +202,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="frames per kernel batch (0 = library default)")
     ap.add_argument("--cpu-frames", type=int, default=4, help="reference frames timed for cpu_baseline (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-slice", type=int, default=64, help="frames per planned/rendered/downloaded slice of the e2e pipeline")
     ap.add_argument("--no-stage-pass", action="store_true",
                     help="profiling runs (under ncu): skip the per-kernel-class timing pass and the e2e leg")
     args = ap.parse_args()
@@ -250,23 +305,45 @@ def main():
     frame_bytes = H * W * 3
     e2e_times, e2e_parts = [], None
     barrier()
+    # The sequence streams through the renderer slice by slice: a planner thread triangulates slice k+1 on the host
+    # cores while slice k renders and slice k-1 is copied to pinned memory (copy stream) - the reference's frame loop
+    # (src/poppy.hpp:172-243) with its three stages overlapped instead of run back to back.
+    import queue
+    import threading
+    slice_frames = max(1, min(F, args.e2e_slice))
+    slices = [(a, min(a + slice_frames, F)) for a in range(0, F, slice_frames)]
     for it in range(0 if args.no_stage_pass else max(args.e2e_steps, 1) + 1):
+        plans = queue.Queue(maxsize=3)
+        plan_busy = [0.0]
+
+        def planner():
+            for a, b in slices:
+                t0 = time.perf_counter()
+                p = host.SequencePlan(inp.pts1, inp.pts2, W, H, phases[a:b], chain=False, threads=plan_threads)
+                plan_busy[0] += time.perf_counter() - t0
+                plans.put((a, b, p))
+
         t_a = time.perf_counter()
-        p = host.SequencePlan(inp.pts1, inp.pts2, W, H, phases, chain=False, threads=plan_threads)
-        t_b = time.perf_counter()
+        th = threading.Thread(target=planner, daemon=True)
+        th.start()
         r.set_pair(h_bgr1.numpy(), h_bgr2.numpy(), h_gab.numpy())
         r.set_points(inp.pts1, inp.pts2)
         t_c = time.perf_counter()
-        r.render(phases, masks, p.tri_idx, p.tri_offsets, chain=False)
-        for first in range(0, F, ring_frames):
-            cnt = min(ring_frames, F - first)
-            r.download_async(first, cnt, h_ring.data_ptr(), W * 3, frame_bytes)
+        for _ in slices:
+            a, b, p = plans.get()
+            r.render(phases[a:b], masks[a:b], p.tri_idx, p.tri_offsets, chain=False, first_slot=a)
+            slot = a % ring_frames
+            if slot + (b - a) > ring_frames:
+                slot = 0
+            r.download_async(a, b - a, h_ring.data_ptr() + slot * frame_bytes, W * 3, frame_bytes)
+            p.close()
         r.sync()
         t_d = time.perf_counter()
-        p.close()
+        th.join()
         if it > 0:        # first pass is warm-up
             e2e_times.append(t_d - t_a)
-            e2e_parts = {"plan_s": t_b - t_a, "h2d_s": t_c - t_b, "render_d2h_s": t_d - t_c, "plan_threads": plan_threads}
+            e2e_parts = {"total_s": t_d - t_a, "h2d_s": t_c - t_a, "planner_busy_s": plan_busy[0], "plan_threads": plan_threads,
+                         "slice_frames": slice_frames, "slices": len(slices)}
     e2e_s = statistics.median(e2e_times) if e2e_times else float("inf")
     h2d_bytes = inp.bgr1.nbytes + inp.bgr2.nbytes + inp.gabor2.nbytes + inp.pts1.nbytes + inp.pts2.nbytes + \
         plan.tri_idx.nbytes + plan.tri_offsets.nbytes + phases.nbytes + masks.nbytes
@@ -291,6 +368,8 @@ def main():
         fps = total_frames / (dev_ms / 1000.0)
         alg = algorithmic_bytes_per_frame(W, H, L)
         peak, peak_src = measured_peaks()
+        traffic = ncu_traffic()
+        chunk_used = args.chunk or 32
         achieved = alg * (fps / world) / 1e9            # per GPU
         kern = []
         tot = sum(v["ms"] for v in stage.values()) or 1.0
@@ -308,10 +387,14 @@ def main():
                        "timing": "CUDA events on the renderer's stream, max over ranks"},
             "e2e": {"value": F * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "breakdown": e2e_parts,
-                    "what": "host Delaunay planning (threads) + H2D pair/points/triangles + render + D2H of every frame to pinned memory"},
+                    "what": "H2D pair/points + per slice: host Delaunay planning (threads), H2D triangles, render, D2H of every frame to "
+                            "pinned memory; the three stages of consecutive slices overlap"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (int(sum(traffic["bytes_per_frame"].values()) * F) if traffic else None),
+                         "traffic_what": "ncu dram__bytes_read+write of all kernels of one step (profiles/ncu_traffic.json)",
+                         "dominant_kernel": dominant_kernel_roofline(kern, W, H, F, chunk_used, peak, traffic, L),
+                         "peak_source": peak_src,
                          "scope": "whole render path per GPU (SURVEY.md 8(d) algorithmic bytes/frame x frames/s)",
                          "algorithmic_bytes_per_frame": alg, "kernels": kern,
                          "stage_timed_step_ms": stage_total_ms},

@@ -94,8 +94,17 @@ int poppy_cuda_set_points(poppy_cuda_ctx* ctx, const float* pts1_xy, const float
 int poppy_cuda_render(poppy_cuda_ctx* ctx, int n_frames, const float* shape_ratio, const double* mask_ratio,
                       const int32_t* tri_idx, const int32_t* tri_offsets, int chain);
 
+/* Same, into ring slots [first_slot, first_slot + n_frames): frame i of the call (arrays indexed from 0) lands in slot
+ * first_slot + i. Lets a caller stream a long sequence through the ring slice by slice - plan slice k+1 on the host
+ * while slice k renders and slice k-1 downloads (the frame loop of src/poppy.hpp:172-243 with the writer hand-off
+ * overlapped). chain == 1 requires first_slot == 0. */
+int poppy_cuda_render_range(poppy_cuda_ctx* ctx, int first_slot, int n_frames, const float* shape_ratio,
+                            const double* mask_ratio, const int32_t* tri_idx, const int32_t* tri_offsets, int chain);
+
 /* Copy frames [first, first+count) (8UC3 BGR) to host memory: row stride `step` bytes, `frame_stride` bytes
- * between frames. Asynchronous if dst is pinned; poppy_cuda_sync() before reading. */
+ * between frames. Ordered after every render queued so far, on a separate copy stream (renders of other slots are not
+ * held up; a render of slots with a download pending waits for it). Asynchronous if dst is pinned;
+ * poppy_cuda_sync() before reading. */
 int poppy_cuda_download(poppy_cuda_ctx* ctx, int first, int count, uint8_t* dst, size_t step, size_t frame_stride);
 
 /* morphedPoints of frame `frame` of the last render (n x 2 float) — the out-parameter of morph_images. */

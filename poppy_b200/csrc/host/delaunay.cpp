@@ -152,6 +152,7 @@ bool DelaunayMesh::begin_walk(Point2f p, Walk& w) const {
     w.p = p;
     w.e = 0;
     w.r_cur = 0;
+    w.on_quad = w.dp_quad = 0;
     w.budget = (int)q_.size() * 4;
     w.where = kOutside;
     if (p.x < top_left_.x || p.y < top_left_.y || p.x >= bottom_right_.x || p.y >= bottom_right_.y) return false;
@@ -171,6 +172,8 @@ bool DelaunayMesh::walk_step(Walk& w) const {
     const int on = qe.next[e & 3], dp = rot(qe.next[(e + 3) & 3], 3);
     const Quad& qon = q[on >> 2];
     const Quad& qdp = q[dp >> 2];
+    w.on_quad = on >> 2;
+    w.dp_quad = dp >> 2;
     const int kon = (on >> 1) & 1, kdp = (dp >> 1) & 1;
     const double a_on = tri_area(p, qon.opt[kon ^ 1], qon.opt[kon]), a_dp = tri_area(p, qdp.opt[kdp ^ 1], qdp.opt[kdp]);
     if (w.r_cur != 0 && a_on != 0 && a_dp != 0) {
@@ -198,6 +201,58 @@ bool DelaunayMesh::walk_step(Walk& w) const {
         w.e = on;
     }
     return true;
+}
+
+namespace {
+// A walk state with everything its step needs already in hand: the edge, its onext / dprev edges, and the coordinate
+// differences (B - p, C - p) of their two orientation predicates tri_area(p, B, C).
+struct WalkCand {
+    int e, on, dp, pad;
+    double on_bx, on_by, on_cx, on_cy, dp_bx, dp_by, dp_cx, dp_cy;
+};
+}  // namespace
+
+bool DelaunayMesh::walk_run(Walk& w, const uint32_t* hint, uint32_t hint_steps, std::vector<uint32_t>* record) const {
+    if (w.r_cur == 0) return false;
+    const Quad* __restrict__ q = q_.data();
+    const double px = w.p.x, py = w.p.y;
+    auto fill = [&](int x, WalkCand& c) {
+        const Quad& qx = q[x >> 2];
+        const int on = qx.next[x & 3], dp = rot(qx.next[(x + 3) & 3], 3);
+        const Quad& qo = q[on >> 2];
+        const Quad& qd = q[dp >> 2];
+        const int ko = (on >> 1) & 1, kd = (dp >> 1) & 1;
+        c.e = x; c.on = on; c.dp = dp;
+        c.on_bx = (double)qo.opt[ko ^ 1].x - px; c.on_by = (double)qo.opt[ko ^ 1].y - py;
+        c.on_cx = (double)qo.opt[ko].x - px;     c.on_cy = (double)qo.opt[ko].y - py;
+        c.dp_bx = (double)qd.opt[kd ^ 1].x - px; c.dp_by = (double)qd.opt[kd ^ 1].y - py;
+        c.dp_cx = (double)qd.opt[kd].x - px;     c.dp_cy = (double)qd.opt[kd].y - py;
+    };
+    constexpr uint32_t kAhead = 6;            // prefetch distance in walk steps
+    WalkCand buf[2][2];
+    fill(w.e, buf[0][0]);
+    const WalkCand* cur = &buf[0][0];
+    uint32_t j = 0;
+    for (int side = 1;; side ^= 1) {
+        if (w.budget <= 0) { w.e = cur->e; w.r_cur = -1; return false; }     // walk_step reports the exhausted budget
+        if (j + kAhead < hint_steps) { prefetch_quad(hint[2 * (j + kAhead)]); prefetch_quad(hint[2 * (j + kAhead) + 1]); }
+        // both successors, speculatively (independent of the predicates below)
+        WalkCand* nxt = buf[side];
+        fill(cur->on, nxt[0]);
+        fill(cur->dp, nxt[1]);
+        const double a_on = cur->on_bx * cur->on_cy - cur->on_by * cur->on_cx;      // tri_area(p, B, C) of onext
+        const double a_dp = cur->dp_bx * cur->dp_cy - cur->dp_by * cur->dp_cx;      // ... of dprev
+        if (a_on == 0 || a_dp == 0) { w.e = cur->e; w.r_cur = -1; return false; }   // degenerate: the generic step decides
+        --w.budget;
+        ++j;
+        if (record) { record->push_back((uint32_t)(cur->on >> 2)); record->push_back((uint32_t)(cur->dp >> 2)); }
+        if (a_on > 0 && a_dp > 0) {
+            w.e = cur->e; w.r_cur = -1; w.where = kInside;
+            w.on_quad = cur->on >> 2; w.dp_quad = cur->dp >> 2;
+            return true;
+        }
+        cur = &nxt[a_on > 0];      // right of onext (then not right of dprev): cross dprev, else onext
+    }
 }
 
 DelaunayMesh::Where DelaunayMesh::classify(const Walk& w, int& out_edge, int& out_vertex) {
@@ -387,7 +442,7 @@ void triangulate_points_batch(const std::vector<Point2f>* sets, int count, int w
 }
 
 bool triangulate_points(std::vector<Point2f> points, int width, int height, std::vector<int32_t>& tri_idx,
-                        std::string* error) {
+                        std::string* error, const WalkTrace* hint, WalkTrace* record) {
     tri_idx.clear();
     clip_points(points, width, height);
     std::vector<Point2f> uniq;
@@ -395,8 +450,35 @@ bool triangulate_points(std::vector<Point2f> points, int width, int height, std:
     make_uniq(points, uniq, &first);
     DelaunayMesh mesh(width, height, (int)uniq.size());
     std::vector<int32_t> owner(4, -1);        // mesh vertex id -> index of its first occurrence in `points`
+    constexpr uint32_t kAhead = 6;            // prefetch distance in walk steps
+    if (record) {
+        record->clear();
+        record->first_step.reserve(uniq.size() + 1);
+        record->quads.reserve(hint && !hint->quads.empty() ? hint->quads.size() + hint->quads.size() / 8 : uniq.size() * 256);
+    }
+    const uint32_t hint_points = hint && !hint->first_step.empty() ? (uint32_t)hint->first_step.size() - 1 : 0;
     for (size_t i = 0; i < uniq.size(); ++i) {
-        const int v = mesh.insert(uniq[i]);
+        DelaunayMesh::Walk w;
+        if (record) record->first_step.push_back((uint32_t)(record->quads.size() / 2));
+        if (mesh.begin_walk(uniq[i], w)) {
+            const uint32_t* h = nullptr;
+            uint32_t hn = 0, j = 0;
+            if (i < hint_points) {
+                h = hint->quads.data() + 2 * (size_t)hint->first_step[i];
+                hn = hint->first_step[i + 1] - hint->first_step[i];
+                for (uint32_t k = 0; k < kAhead && k < hn; ++k) { mesh.prefetch_quad(h[2 * k]); mesh.prefetch_quad(h[2 * k + 1]); }
+            }
+            // general-position stretches run in the dependence-cut loop; a degenerate predicate is decided by one
+            // generic step, after which the fast loop resumes
+            while (!mesh.walk_run(w, h ? h + 2 * (size_t)j : nullptr, j < hn ? hn - j : 0, record ? &record->quads : nullptr)) {
+                if (record) j = (uint32_t)(record->quads.size() / 2) - record->first_step.back();
+                const bool more = mesh.walk_step(w);
+                if (record) { record->quads.push_back((uint32_t)w.on_quad); record->quads.push_back((uint32_t)w.dp_quad); }
+                ++j;
+                if (!more) break;
+            }
+        }
+        const int v = mesh.finish_insert(w);
         if (v < 0) {
             if (error) *error = mesh.error();
             return false;
@@ -404,6 +486,7 @@ bool triangulate_points(std::vector<Point2f> points, int width, int height, std:
         if (v >= (int)owner.size()) owner.resize(v + 1, -1);
         if (owner[v] < 0) owner[v] = first[i];
     }
+    if (record) record->first_step.push_back((uint32_t)(record->quads.size() / 2));
     std::vector<int32_t> ids;
     mesh.triangles(ids);
     tri_idx.resize(ids.size());

@@ -45,6 +45,11 @@ struct poppy_cuda_ctx {
     int n_points = 0, last_frames = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // downloads run on their own stream so that they overlap the render of other ring slots; a render that would
+    // overwrite slots with a download pending waits for it
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_rendered = nullptr, ev_copied = nullptr;
+    int copy_lo = 0, copy_hi = 0;        // ring slots [lo, hi) with a download enqueued since the last sync
     std::string err;
     uint64_t launches = 0;
 
@@ -205,7 +210,7 @@ void collect_timing(poppy_cuda_ctx* c) {
     c->timed.clear();
 }
 
-int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const double* mask, const int32_t* tri_idx,
+int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* shape, const double* mask, const int32_t* tri_idx,
                  const int32_t* tri_off, bool chain, poppy_cuda_ctx::Lane& ln) {
     cudaStream_t st = ln.stream;
     CU_TRY(c, cudaEventSynchronize(ln.ev_staged));       // the lane's staging buffers are free again
@@ -229,7 +234,7 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
         p.amount = (float)(1.0 - std::sin(mask[f] * M_PI));
         p.n_tri = nt;
         p.tri_base = tri_total;
-        p.dst_slot = f;
+        p.dst_slot = slot0 + f;
         tri_total += nt;
         tri_max = std::max(tri_max, nt);
     }
@@ -240,7 +245,7 @@ int render_chunk(poppy_cuda_ctx* c, int first, int nb, const float* shape, const
     const bool chained = chain && first > 0;
     const float2* p1 = chained ? c->d_morphed + (size_t)(first - 1) * c->max_points : c->d_pts1;
     const cudaTextureObject_t src1 = chained ? c->t_src[2] : c->t_src[0];
-    float2* morphed = c->d_morphed + (size_t)first * c->max_points;
+    float2* morphed = c->d_morphed + (size_t)(slot0 + first) * c->max_points;
     const int n = c->n_points, w = c->w, h = c->h, L = c->levels;
 
     {   Scope s(c, KC_POINTS, st);
@@ -332,6 +337,9 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
     CR_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CR_TRY(cudaEventCreate(&c->ev_begin));
     CR_TRY(cudaEventCreate(&c->ev_end));
+    CR_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CR_TRY(cudaEventCreateWithFlags(&c->ev_rendered, cudaEventDisableTiming));
+    CR_TRY(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
     for (auto& l : c->lane) {
         CR_TRY(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         CR_TRY(cudaEventCreateWithFlags(&l.ev_staged, cudaEventDisableTiming));
@@ -392,6 +400,7 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (auto& l : c->lane) if (l.stream) cudaStreamSynchronize(l.stream);
     collect_timing(c);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
@@ -405,6 +414,9 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
     cudaFree(c->d_frames); cudaFree(c->d_sum);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto& l : c->lane) {
         if (l.ev_staged) cudaEventDestroy(l.ev_staged);
         if (l.ev_done) cudaEventDestroy(l.ev_done);
@@ -509,12 +521,21 @@ int poppy_cuda_set_points(poppy_cuda_ctx* c, const float* pts1, const float* pts
 
 int poppy_cuda_render(poppy_cuda_ctx* c, int n_frames, const float* shape, const double* mask, const int32_t* tri_idx,
                       const int32_t* tri_off, int chain) {
+    return poppy_cuda_render_range(c, 0, n_frames, shape, mask, tri_idx, tri_off, chain);
+}
+
+int poppy_cuda_render_range(poppy_cuda_ctx* c, int first_slot, int n_frames, const float* shape, const double* mask,
+                            const int32_t* tri_idx, const int32_t* tri_off, int chain) {
     if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (first_slot < 0 || (chain && first_slot != 0)) return fail(c, POPPY_CUDA_ERR_INVALID, "bad first_slot %d (a chain starts at slot 0)", first_slot);
     if (!c->have_pair || !c->have_points) return fail(c, POPPY_CUDA_ERR_STATE, "set_pair and set_points must precede render");
     if (!shape || !mask || !tri_idx || !tri_off) return fail(c, POPPY_CUDA_ERR_INVALID, "null argument");
-    if (n_frames < 1 || n_frames > c->max_frames) return fail(c, POPPY_CUDA_ERR_CAPACITY, "%d frames (max %d)", n_frames, c->max_frames);
+    if (n_frames < 1 || first_slot + n_frames > c->max_frames)
+        return fail(c, POPPY_CUDA_ERR_CAPACITY, "frames [%d, %d) exceed the ring (max %d)", first_slot, first_slot + n_frames, c->max_frames);
     CU_TRY(c, cudaSetDevice(c->device));
     if (int rc = ensure_chunk(c)) return rc;
+    if (first_slot < c->copy_hi && first_slot + n_frames > c->copy_lo)      // slots with a download in flight
+        CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
     collect_timing(c);
     std::fill(c->class_ms, c->class_ms + KC_COUNT, 0.f);
     std::fill(c->class_launches, c->class_launches + KC_COUNT, 0ull);
@@ -527,14 +548,14 @@ int poppy_cuda_render(poppy_cuda_ctx* c, int n_frames, const float* shape, const
     int k = 0;
     for (int first = 0; first < n_frames; first += B, ++k) {
         const int nb = std::min(B, n_frames - first);
-        if (int rc = render_chunk(c, first, nb, shape, mask, tri_idx, tri_off, chain != 0, c->lane[k % lanes])) return rc;
+        if (int rc = render_chunk(c, first_slot, first, nb, shape, mask, tri_idx, tri_off, chain != 0, c->lane[k % lanes])) return rc;
     }
     for (int i = 0; i < lanes; ++i) {
         CU_TRY(c, cudaEventRecord(c->lane[i].ev_done, c->lane[i].stream));
         CU_TRY(c, cudaStreamWaitEvent(c->stream, c->lane[i].ev_done, 0));
     }
     CU_TRY(c, cudaEventRecord(c->ev_end, c->stream));
-    c->last_frames = n_frames;
+    c->last_frames = first_slot + n_frames;
     return 0;
 }
 
@@ -544,14 +565,21 @@ int poppy_cuda_download(poppy_cuda_ctx* c, int first, int count, uint8_t* dst, s
     if (!dst || first < 0 || count < 1 || first + count > c->max_frames || step < row || frame_stride < step * c->h)
         return fail(c, POPPY_CUDA_ERR_INVALID, "bad download range or strides");
     CU_TRY(c, cudaSetDevice(c->device));
+    // after everything queued on the context's stream so far (the renders that produce these slots), but on the copy
+    // stream: later renders of other slots are not held up by the transfer
+    CU_TRY(c, cudaEventRecord(c->ev_rendered, c->stream));
+    CU_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered, 0));
     if (step == row && frame_stride == c->frame_bytes()) {
         CU_TRY(c, cudaMemcpyAsync(dst, c->d_frames + (size_t)first * c->frame_bytes(), (size_t)count * c->frame_bytes(),
-                                  cudaMemcpyDeviceToHost, c->stream));
+                                  cudaMemcpyDeviceToHost, c->copy_stream));
     } else {
         for (int i = 0; i < count; ++i)
             CU_TRY(c, cudaMemcpy2DAsync(dst + (size_t)i * frame_stride, step, c->d_frames + (size_t)(first + i) * c->frame_bytes(),
-                                        row, row, c->h, cudaMemcpyDeviceToHost, c->stream));
+                                        row, row, c->h, cudaMemcpyDeviceToHost, c->copy_stream));
     }
+    CU_TRY(c, cudaEventRecord(c->ev_copied, c->copy_stream));
+    if (c->copy_hi <= c->copy_lo) { c->copy_lo = first; c->copy_hi = first + count; }
+    else { c->copy_lo = std::min(c->copy_lo, first); c->copy_hi = std::max(c->copy_hi, first + count); }
     return 0;
 }
 
@@ -591,6 +619,8 @@ int poppy_cuda_sync(poppy_cuda_ctx* c) {
     if (!c) return POPPY_CUDA_ERR_INVALID;
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->copy_stream));
+    c->copy_lo = c->copy_hi = 0;
     return 0;
 }
 

@@ -87,8 +87,8 @@ class MorphRenderer:
         self.n_points = pts1.shape[0]
 
     # -- render --------------------------------------------------------------------------------------------------
-    def render(self, shape_ratio, mask_ratio, tri_idx, tri_offsets, chain=False):
-        """Render len(shape_ratio) frames into the HBM ring. tri_idx: (sum T_f) x 3 int32, tri_offsets: F+1."""
+    def render(self, shape_ratio, mask_ratio, tri_idx, tri_offsets, chain=False, first_slot=0):
+        """Render len(shape_ratio) frames into ring slots first_slot.. . tri_idx: (sum T_f) x 3 int32, tri_offsets: F+1."""
         shape_ratio = np.ascontiguousarray(shape_ratio, np.float32)
         mask_ratio = np.ascontiguousarray(mask_ratio, np.float64)
         tri_idx = np.ascontiguousarray(tri_idx, np.int32).reshape(-1, 3)
@@ -96,8 +96,8 @@ class MorphRenderer:
         n = shape_ratio.shape[0]
         if mask_ratio.shape[0] != n or tri_offsets.shape[0] != n + 1 or tri_offsets[-1] != tri_idx.shape[0]:
             raise ValueError("inconsistent frame / triangle-offset arrays")
-        self._check(self._lib.poppy_cuda_render(self._ctx, n, _ptr(shape_ratio), _ptr(mask_ratio), _ptr(tri_idx),
-                                                _ptr(tri_offsets), 1 if chain else 0))
+        self._check(self._lib.poppy_cuda_render_range(self._ctx, int(first_slot), n, _ptr(shape_ratio), _ptr(mask_ratio),
+                                                      _ptr(tri_idx), _ptr(tri_offsets), 1 if chain else 0))
         return n
 
     def download(self, first, count, out: np.ndarray | None = None) -> np.ndarray:

@@ -183,3 +183,40 @@ def test_error_behaviour(native_lib):
             r.set_points(np.zeros((100, 2), np.float32), np.zeros((100, 2), np.float32))   # > max_points
     with pytest.raises(PoppyCudaError):
         MorphRenderer(40000, 10, 3, 32, 64, 1)                       # cv::remap size limit
+
+
+def test_render_range_streams_slices_through_the_ring(native_lib):
+    """poppy_cuda_render_range: a sequence rendered slice by slice into consecutive ring slots, with the download of
+    each slice overlapping the next render (copy stream), equals the one-call render; re-rendering slots whose download
+    is still pending waits for it."""
+    from poppy_b200.renderer import MorphRenderer
+    w, h, levels, F = 320, 200, 5, 12
+    inp = synth.make_inputs(w, h, 90, 6.0, seed=21)
+    phases = np.linspace(0.0, 1.0, F).astype(np.float32)
+    masks = phases.astype(np.float64)
+    plan = host.SequencePlan(inp.pts1, inp.pts2, w, h, phases)
+    with MorphRenderer(w, h, levels, len(inp.pts1), plan.max_triangles, F, chunk_frames=2) as r:
+        r.set_pair(inp.bgr1, inp.bgr2, inp.gabor2)
+        r.set_points(inp.pts1, inp.pts2)
+        r.render(phases, masks, plan.tri_idx, plan.tri_offsets)
+        want = r.download(0, F)
+        want_pts = [r.morphed_points(k) for k in range(F)]
+        got = np.zeros_like(want)
+        for a in range(0, F, 5):                                   # ragged slices: 5, 5, 2
+            b = min(a + 5, F)
+            p = host.SequencePlan(inp.pts1, inp.pts2, w, h, phases[a:b])
+            r.render(phases[a:b], masks[a:b], p.tri_idx, p.tri_offsets, first_slot=a)
+            r.download_async(a, b - a, got[a:].ctypes.data, w * 3, w * h * 3)
+        r.sync()
+        assert bits_differ(got, want) == 0
+        for k in range(F):
+            assert bits_differ(r.morphed_points(k), want_pts[k]) == 0
+        # overwrite slots 0..4 with other phases while their download is pending, then read them back
+        r.download_async(0, 5, got.ctypes.data, w * 3, w * h * 3)
+        p = host.SequencePlan(inp.pts1, inp.pts2, w, h, phases[5:10])
+        r.render(phases[5:10], masks[5:10], p.tri_idx, p.tri_offsets, first_slot=0)
+        r.sync()
+        assert bits_differ(got[:5], want[:5]) == 0                 # the pending download saw the old frames
+        assert bits_differ(r.download(0, 5), want[5:10]) == 0
+        with pytest.raises(Exception):
+            r.render(phases[:5], masks[:5], plan.tri_idx[:plan.tri_offsets[5]], plan.tri_offsets[:6], first_slot=F - 2)

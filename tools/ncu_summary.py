@@ -77,5 +77,33 @@ def full(path):
                 print(f"   {k:85s} {d[k]:>16s} {u.get(k, '')}")
 
 
+CLASS_OF = [("k_raster_warp", "raster_warp"), ("k_pyr_down", "pyr_down"), ("k_collapse_roll", "blend_collapse"),
+            ("k_blend_coarsest", "blend_collapse"), ("k_unsharp", "unsharp_store"), ("k_tri_geometry", "tri_geometry"),
+            ("k_bin_", "bin_triangles"), ("k_lerp_points", "lerp_points")]
+
+
+def traffic(path, frames):
+    """JSON for profiles/ncu_traffic.json: DRAM bytes per frame of each kernel class of one chunk of `frames` frames."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    agg = {}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
+        name = short(d["Kernel Name"])
+        cls = next((c for k, c in CLASS_OF if k in name), None)
+        if not cls:
+            continue
+        b = sum(float(d[k].replace(",", "")) * scale[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        agg[cls] = agg.get(cls, 0.0) + b / frames
+    print(json.dumps({"source": f"ncu --set full --clock-control none, one {frames}-frame chunk ({path})",
+                      "bytes_per_frame": {k: round(v) for k, v in agg.items()}}, indent=1))
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], int(sys.argv[3]))
+        sys.exit(0)
     {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
