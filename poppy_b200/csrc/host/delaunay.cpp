@@ -152,7 +152,6 @@ bool DelaunayMesh::begin_walk(Point2f p, Walk& w) const {
     w.p = p;
     w.e = 0;
     w.r_cur = 0;
-    w.on_quad = w.dp_quad = 0;
     w.budget = (int)q_.size() * 4;
     w.where = kOutside;
     if (p.x < top_left_.x || p.y < top_left_.y || p.x >= bottom_right_.x || p.y >= bottom_right_.y) return false;
@@ -172,8 +171,6 @@ bool DelaunayMesh::walk_step(Walk& w) const {
     const int on = qe.next[e & 3], dp = rot(qe.next[(e + 3) & 3], 3);
     const Quad& qon = q[on >> 2];
     const Quad& qdp = q[dp >> 2];
-    w.on_quad = on >> 2;
-    w.dp_quad = dp >> 2;
     const int kon = (on >> 1) & 1, kdp = (dp >> 1) & 1;
     const double a_on = tri_area(p, qon.opt[kon ^ 1], qon.opt[kon]), a_dp = tri_area(p, qdp.opt[kdp ^ 1], qdp.opt[kdp]);
     if (w.r_cur != 0 && a_on != 0 && a_dp != 0) {
@@ -212,7 +209,7 @@ struct WalkCand {
 };
 }  // namespace
 
-bool DelaunayMesh::walk_run(Walk& w, const uint32_t* hint, uint32_t hint_steps, std::vector<uint32_t>* record) const {
+bool DelaunayMesh::walk_run(Walk& w) const {
     if (w.r_cur == 0) return false;
     const Quad* __restrict__ q = q_.data();
     const double px = w.p.x, py = w.p.y;
@@ -228,14 +225,11 @@ bool DelaunayMesh::walk_run(Walk& w, const uint32_t* hint, uint32_t hint_steps, 
         c.dp_bx = (double)qd.opt[kd ^ 1].x - px; c.dp_by = (double)qd.opt[kd ^ 1].y - py;
         c.dp_cx = (double)qd.opt[kd].x - px;     c.dp_cy = (double)qd.opt[kd].y - py;
     };
-    constexpr uint32_t kAhead = 6;            // prefetch distance in walk steps
     WalkCand buf[2][2];
     fill(w.e, buf[0][0]);
     const WalkCand* cur = &buf[0][0];
-    uint32_t j = 0;
     for (int side = 1;; side ^= 1) {
         if (w.budget <= 0) { w.e = cur->e; w.r_cur = -1; return false; }     // walk_step reports the exhausted budget
-        if (j + kAhead < hint_steps) { prefetch_quad(hint[2 * (j + kAhead)]); prefetch_quad(hint[2 * (j + kAhead) + 1]); }
         // both successors, speculatively (independent of the predicates below)
         WalkCand* nxt = buf[side];
         fill(cur->on, nxt[0]);
@@ -244,11 +238,8 @@ bool DelaunayMesh::walk_run(Walk& w, const uint32_t* hint, uint32_t hint_steps, 
         const double a_dp = cur->dp_bx * cur->dp_cy - cur->dp_by * cur->dp_cx;      // ... of dprev
         if (a_on == 0 || a_dp == 0) { w.e = cur->e; w.r_cur = -1; return false; }   // degenerate: the generic step decides
         --w.budget;
-        ++j;
-        if (record) { record->push_back((uint32_t)(cur->on >> 2)); record->push_back((uint32_t)(cur->dp >> 2)); }
         if (a_on > 0 && a_dp > 0) {
             w.e = cur->e; w.r_cur = -1; w.where = kInside;
-            w.on_quad = cur->on >> 2; w.dp_quad = cur->dp >> 2;
             return true;
         }
         cur = &nxt[a_on > 0];      // right of onext (then not right of dprev): cross dprev, else onext
@@ -282,8 +273,12 @@ DelaunayMesh::Where DelaunayMesh::classify(const Walk& w, int& out_edge, int& ou
 
 int DelaunayMesh::insert(Point2f p) {
     Walk w;
-    if (begin_walk(p, w))
-        while (walk_step(w)) {}
+    if (begin_walk(p, w)) {
+        // general-position stretches run in the dependence-cut loop; a degenerate predicate is decided by one generic
+        // step, after which the fast loop resumes
+        while (!walk_run(w))
+            if (!walk_step(w)) break;
+    }
     return finish_insert(w);
 }
 
@@ -442,7 +437,7 @@ void triangulate_points_batch(const std::vector<Point2f>* sets, int count, int w
 }
 
 bool triangulate_points(std::vector<Point2f> points, int width, int height, std::vector<int32_t>& tri_idx,
-                        std::string* error, const WalkTrace* hint, WalkTrace* record) {
+                        std::string* error) {
     tri_idx.clear();
     clip_points(points, width, height);
     std::vector<Point2f> uniq;
@@ -450,35 +445,8 @@ bool triangulate_points(std::vector<Point2f> points, int width, int height, std:
     make_uniq(points, uniq, &first);
     DelaunayMesh mesh(width, height, (int)uniq.size());
     std::vector<int32_t> owner(4, -1);        // mesh vertex id -> index of its first occurrence in `points`
-    constexpr uint32_t kAhead = 6;            // prefetch distance in walk steps
-    if (record) {
-        record->clear();
-        record->first_step.reserve(uniq.size() + 1);
-        record->quads.reserve(hint && !hint->quads.empty() ? hint->quads.size() + hint->quads.size() / 8 : uniq.size() * 256);
-    }
-    const uint32_t hint_points = hint && !hint->first_step.empty() ? (uint32_t)hint->first_step.size() - 1 : 0;
     for (size_t i = 0; i < uniq.size(); ++i) {
-        DelaunayMesh::Walk w;
-        if (record) record->first_step.push_back((uint32_t)(record->quads.size() / 2));
-        if (mesh.begin_walk(uniq[i], w)) {
-            const uint32_t* h = nullptr;
-            uint32_t hn = 0, j = 0;
-            if (i < hint_points) {
-                h = hint->quads.data() + 2 * (size_t)hint->first_step[i];
-                hn = hint->first_step[i + 1] - hint->first_step[i];
-                for (uint32_t k = 0; k < kAhead && k < hn; ++k) { mesh.prefetch_quad(h[2 * k]); mesh.prefetch_quad(h[2 * k + 1]); }
-            }
-            // general-position stretches run in the dependence-cut loop; a degenerate predicate is decided by one
-            // generic step, after which the fast loop resumes
-            while (!mesh.walk_run(w, h ? h + 2 * (size_t)j : nullptr, j < hn ? hn - j : 0, record ? &record->quads : nullptr)) {
-                if (record) j = (uint32_t)(record->quads.size() / 2) - record->first_step.back();
-                const bool more = mesh.walk_step(w);
-                if (record) { record->quads.push_back((uint32_t)w.on_quad); record->quads.push_back((uint32_t)w.dp_quad); }
-                ++j;
-                if (!more) break;
-            }
-        }
-        const int v = mesh.finish_insert(w);
+        const int v = mesh.insert(uniq[i]);
         if (v < 0) {
             if (error) *error = mesh.error();
             return false;
@@ -486,7 +454,6 @@ bool triangulate_points(std::vector<Point2f> points, int width, int height, std:
         if (v >= (int)owner.size()) owner.resize(v + 1, -1);
         if (owner[v] < 0) owner[v] = first[i];
     }
-    if (record) record->first_step.push_back((uint32_t)(record->quads.size() / 2));
     std::vector<int32_t> ids;
     mesh.triangles(ids);
     tri_idx.resize(ids.size());

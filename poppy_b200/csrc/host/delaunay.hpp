@@ -41,12 +41,7 @@ public:
         Point2f p;
         int e, r_cur, budget;
         Where where;
-        int on_quad, dp_quad;     // quad records of onext / dprev read by the last walk_step (prefetch hints, see WalkTrace)
     };
-    // hint only: pull a quad record towards the core (no effect on any result)
-    void prefetch_quad(uint32_t quad) const {
-        if (quad < q_.size()) __builtin_prefetch(&q_[quad], 0, 3);
-    }
 
     // The same insertion cut at the boundaries of its point-location walk, so that a caller can advance the walks of
     // several independent meshes in one instruction stream (triangulate_points_batch): the walk is a chain of dependent
@@ -64,8 +59,7 @@ public:
     // being loaded and their coordinate differences formed, so a step costs one predicate latency instead of
     // load -> load -> predicate. Identical decisions to walk_step (same double arithmetic, same order); stops at the
     // first degenerate predicate. Returns true when the walk ended (w.where set), false when walk_step must continue.
-    // hint/hint_steps: quads to prefetch (WalkTrace of an earlier frame); record: receives (onext, dprev) quads per step.
-    bool walk_run(Walk& w, const uint32_t* hint, uint32_t hint_steps, std::vector<uint32_t>* record) const;
+    bool walk_run(Walk& w) const;
 
     // Subdiv2D::getTriangleList order; each triangle as three vertex ids (all >= 4).
     void triangles(std::vector<int32_t>& vertex_ids) const;
@@ -114,24 +108,11 @@ private:
     std::string err_;
 };
 
-// Quad records touched by the point-location walks of one triangulation, in insertion order. Consecutive frames of a
-// morph move every point by a fraction of a pixel, so the walks of frame k+1 visit almost the same records as those of
-// frame k: replayed a few steps ahead as software prefetches they turn the walk's dependent cache misses (its whole
-// cost: two dependent L2 accesses per step) into L1 hits. The trace is a HINT: the walk itself is unchanged, a stale
-// or foreign trace only wastes prefetches.
-struct WalkTrace {
-    std::vector<uint32_t> first_step;     // per inserted point: index of its first step in `quads` / 2
-    std::vector<uint32_t> quads;          // per step: quad of onext, quad of dprev
-    void clear() { first_step.clear(); quads.clear(); }
-};
-
 // The host stage of morph_images for one frame (reference src/algo.cpp:205-213): clip, dedupe, triangulate, and
 // return triangle vertex indices into `points` (first exact-equal occurrence), in getTriangleList order.
 // Returns false (with `error`) where the reference would throw.
-// hint (nullable): trace of a similar, earlier triangulation to prefetch along; record (nullable): receives this
-// triangulation's trace.
 bool triangulate_points(std::vector<Point2f> points, int width, int height, std::vector<int32_t>& tri_idx,
-                        std::string* error = nullptr, const WalkTrace* hint = nullptr, WalkTrace* record = nullptr);
+                        std::string* error = nullptr);
 
 // The same for `count` independent point sets (the frames of a sequence) on one thread, with the point-location walks
 // of up to `ways` meshes interleaved (see DelaunayMesh::walk_step). ok[i] / errors[i] as triangulate_points.

@@ -5,7 +5,6 @@
 #include <cstring>
 #include <functional>
 #include <memory>
-#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -18,27 +17,6 @@ using poppy::Point2f;
 
 namespace {
 thread_local std::string g_host_error;
-
-// Walk traces that survive a planning call (one per concurrent worker): see poppy::WalkTrace.
-struct TraceSlot {
-    poppy::WalkTrace a, b;
-    bool busy = false;
-};
-std::mutex g_trace_mu;
-std::vector<std::unique_ptr<TraceSlot>> g_trace_slots;
-
-TraceSlot* acquire_trace_slot() {
-    std::lock_guard<std::mutex> lock(g_trace_mu);
-    for (auto& s : g_trace_slots)
-        if (!s->busy) { s->busy = true; return s.get(); }
-    g_trace_slots.emplace_back(new TraceSlot());
-    g_trace_slots.back()->busy = true;
-    return g_trace_slots.back().get();
-}
-void release_trace_slot(TraceSlot* s) {
-    std::lock_guard<std::mutex> lock(g_trace_mu);
-    s->busy = false;
-}
 
 int host_fail(int code, const std::string& msg) {
     g_host_error = msg;
@@ -134,23 +112,15 @@ int poppy_host_plan_create(poppy_host_plan** out, const float* p1, const float* 
     // (pays where the quad-edge tables of several meshes fit the core's cache; see delaunay.hpp)
     const char* ways_env = std::getenv("POPPY_PLAN_WAYS");
     const int ways = ways_env ? std::max(1, std::min(8, std::atoi(ways_env))) : 1;
-    // ways == 1 (default): every worker prefetches along the walk trace of the frame it triangulated before (WalkTrace,
-    // delaunay.hpp); the traces outlive the call, so a sequence planned slice by slice keeps its hints.
-    // POPPY_PLAN_HINTS=0 switches the hints off.
-    const char* hints_env = std::getenv("POPPY_PLAN_HINTS");
-    const bool hints = ways == 1 && !(hints_env && hints_env[0] == '0');
-    auto work_hinted = [&] {
-        TraceSlot* slot = acquire_trace_slot();
-        poppy::WalkTrace *prev = &slot->a, *cur = &slot->b;
+    // ways == 1 (default): one frame at a time per worker, with the dependence-cut point-location loop
+    // (DelaunayMesh::walk_run); POPPY_PLAN_WAYS > 1 selects the interleaved multi-frame walks instead
+    auto work_single = [&] {
         for (int f; (f = next.fetch_add(1)) < n_frames;) {
-            if (!poppy::triangulate_points(plan->points[f], w, h, tris[f], &errs[f], prev, cur)) {
+            if (!poppy::triangulate_points(plan->points[f], w, h, tris[f], &errs[f])) {
                 int expected = -1;
                 failed.compare_exchange_strong(expected, f);
             }
-            std::swap(prev, cur);
         }
-        if (prev != &slot->a) std::swap(slot->a, slot->b);      // the newest trace waits in `a` for the next call
-        release_trace_slot(slot);
     };
     auto work_batched = [&] {
         std::unique_ptr<bool[]> ok(new bool[ways]);
@@ -165,7 +135,7 @@ int poppy_host_plan_create(poppy_host_plan** out, const float* p1, const float* 
         }
     };
     std::function<void()> work = work_batched;
-    if (hints) work = work_hinted;
+    if (ways == 1) work = work_single;
     std::vector<std::thread> pool;
     for (int i = 1; i < nt; ++i) pool.emplace_back(work);
     work();
