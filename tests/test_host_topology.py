@@ -91,3 +91,23 @@ def test_sequence_plan_direct_and_chain(native_lib):
         cur = host.morph_points(cur, inp.pts2, float(ratios[f]), 200, 150)
         assert bits_differ(chain.points(f), cur) == 0
         assert (chain.triangles(f) == host.triangulate(cur, 200, 150)).all()
+
+
+@pytest.mark.skipif(not ref.available(), reason="reference library not built")
+@pytest.mark.parametrize("kind", ["uniform", "lattice", "clustered"])
+def test_triangulation_matches_reference_at_scale(native_lib, kind):
+    """Long point-location walks (thousands of points): the dependence-cut walk loop (DelaunayMesh::walk_run) with its
+    hand-over to the generic step at degenerate predicates must reproduce cv::Subdiv2D's triangle list exactly."""
+    rng = np.random.default_rng(123)
+    w, h, n = 1920, 1080, 6000
+    if kind == "uniform":
+        p = np.stack([rng.uniform(2, w - 3, n), rng.uniform(2, h - 3, n)], 1)
+    elif kind == "lattice":        # collinear runs, points on edges, duplicates
+        p = np.stack([rng.integers(0, 96, n) * 20, rng.integers(0, 54, n) * 20], 1)
+    else:
+        c = rng.uniform(100, 900, (12, 2))
+        p = c[rng.integers(0, 12, n)] + rng.normal(0, 25, (n, 2))
+        p = np.clip(p, 0, [w - 1, h - 1])
+    p = p.astype(np.float32)
+    a, b = ref.triangulate(w, h, p), host.triangulate(p, w, h)
+    assert a.shape == b.shape and (a == b).all(), kind
