@@ -204,7 +204,7 @@ __device__ __forceinline__ bool down_pair_interior(int xo, int sw, int dw, unsig
 
 // block (32, 4); grid (ceil(dw/128), ceil(dh/64), frames * 7): blockIdx.z is the plane job f*7+p, whose planes start
 // at job * stride in both levels. Warp wy of a CTA produces output rows (blockIdx.y*4 + wy)*16 .. +15.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 12)      // 40 registers: the walk is latency-bound, residency pays more than the few spills
 k_pyr_down_roll(const float* __restrict__ src, int sw, int sh, int spitch, size_t sstride, float* __restrict__ dst, int dw,
                 int dh, int dpitch, size_t dstride) {
     const int job = blockIdx.z, p = job % 7, lane = threadIdx.x;
