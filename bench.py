@@ -300,7 +300,7 @@ def main():
         r._check(r._lib.poppy_cuda_set_stage_timing(r._ctx, 0))
 
     # ---- e2e: the public-API path with host buffers --------------------------------------------------------------
-    ring_frames = min(F, 64)
+    ring_frames = min(F, max(64, args.e2e_slice))        # pinned host ring: at least one slice
     h_ring = torch.empty((ring_frames, H, W, 3), dtype=torch.uint8).pin_memory()
     frame_bytes = H * W * 3
     e2e_times, e2e_parts = [], None
