@@ -345,6 +345,24 @@ def main():
             e2e_parts = {"total_s": t_d - t_a, "h2d_s": t_c - t_a, "planner_busy_s": plan_busy[0], "plan_threads": plan_threads,
                          "slice_frames": slice_frames, "slices": len(slices)}
     e2e_s = statistics.median(e2e_times) if e2e_times else float("inf")
+
+    # ---- the drop-in call itself: one morph_images() per frame, exactly the reference's signature and calling pattern
+    # (src/poppy.hpp:215: images, points and ratios in, dst and morphedPoints out; every call uploads the pair,
+    # triangulates on ONE host thread, renders one frame and downloads it)
+    single_call = None
+    if rank == 0 and world == 1 and not args.no_stage_pass and args.e2e_steps > 0:
+        from poppy_b200 import api
+        api.Settings.instance().pyramid_levels = L
+        ts = []
+        for k in range(5):
+            sk = float(phases[(k * 131) % F])
+            t0 = time.perf_counter()
+            api.morph_images(inp.bgr1, inp.bgr2, inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, sk, sk)
+            ts.append(time.perf_counter() - t0)
+        api.release()
+        single_call = {"value": 1.0 / statistics.median(ts[1:]), "unit": "frames/s",
+                       "what": "poppy_b200.api.morph_images() called once per frame (pair H2D + single-thread Delaunay + "
+                               "render + D2H per call), the reference's own calling pattern"}
     h2d_bytes = inp.bgr1.nbytes + inp.bgr2.nbytes + inp.gabor2.nbytes + inp.pts1.nbytes + inp.pts2.nbytes + \
         plan.tri_idx.nbytes + plan.tri_offsets.nbytes + phases.nbytes + masks.nbytes
     d2h_bytes = F * frame_bytes
@@ -386,7 +404,7 @@ def main():
                        "l2_policy": "inputs larger than L2: each step streams >100 GB through HBM scratch + frame ring",
                        "timing": "CUDA events on the renderer's stream, max over ranks"},
             "e2e": {"value": F * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h_bytes), "breakdown": e2e_parts,
+                    "d2h_bytes_per_step": int(d2h_bytes), "breakdown": e2e_parts, "single_call": single_call,
                     "what": "H2D pair/points + per slice: host Delaunay planning (threads), H2D triangles, render, D2H of every frame to "
                             "pinned memory; the three stages of consecutive slices overlap"},
             "gpu_launches": launches,
