@@ -660,7 +660,20 @@ struct __align__(16) CollapseStage {       // one step of one warp
     float cm[3][32];                       //                                         column a-1
     float cp[3][32];                       //                                         column a+2
 };
-constexpr size_t CL_SMEM = sizeof(CollapseStage) * CL_STAGES * 3;
+// TMA variant of the staging (tiles whose 72-column coarse segment lies inside the row pitch): lane 0 fills a stage with
+// nine cp.async.bulk row segments (6 fine rows of 512 B, 3 coarse rows of 288 B) that complete on the stage's mbarrier,
+// instead of 15 LDGSTS instructions from every lane; the LSU only sees the shared-memory reads.
+struct __align__(128) CollapseBulkStage {
+    float fine[6][128];                    // rows fy, fy+1: (image 1 | left, image 2 | right, mask) x 2; [3 * r + i]
+    float coarse[3][72];                   // coarse row sy+1 of (left, right, out): columns a0 - 4 .. a0 + 67
+};
+struct __align__(128) CollapseBulkRing {   // one per warp
+    CollapseBulkStage st[CL_STAGES];
+    unsigned long long bar[CL_STAGES];
+};
+constexpr unsigned CL_BULK_BYTES = 6 * 512 + 3 * 288;
+constexpr size_t CL_SMEM_LDGSTS = sizeof(CollapseStage) * CL_STAGES * 3, CL_SMEM_BULK = sizeof(CollapseBulkRing) * 3;
+constexpr size_t CL_SMEM = CL_SMEM_LDGSTS > CL_SMEM_BULK ? CL_SMEM_LDGSTS : CL_SMEM_BULK;
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
@@ -728,6 +741,12 @@ __device__ __forceinline__ void fine_unpack(const FineRaw<false>& r, int c, floa
     mk[0] = r.m.x; mk[1] = r.m.y; mk[2] = r.m.z; mk[3] = r.m.w;
 }
 
+__device__ __forceinline__ void fine_from_rows(float4 a, float4 b, float4 m, FineRaw<true>& f) {
+    f.a = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+    f.b = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+    f.m = m;
+}
+__device__ __forceinline__ void fine_from_rows(float4 l, float4 r, float4 m, FineRaw<false>& f) { f.l = l; f.r = r; f.m = m; }
 __device__ __forceinline__ void fine_from_stage(const CollapseStage& S, int r, int lane, FineRaw<true>& f) {
     const float4 a = S.fine[3 * r + 0][lane], b = S.fine[3 * r + 1][lane];
     f.a = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
@@ -739,8 +758,9 @@ __device__ __forceinline__ void fine_from_stage(const CollapseStage& S, int r, i
 }
 
 // One warp = one colour channel c of a 128 x 32 fine tile. `stages`: this warp's CL_STAGES staging slots.
-template <bool L0, bool INTERIOR>
-__device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int fx, int cy0, CollapseStage* stages, int lane) {
+template <bool L0, bool INTERIOR, bool BULK = false>
+__device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int fx, int cy0, CollapseStage* stages, int lane,
+                                              CollapseBulkRing* ring = nullptr) {
     const float* __restrict__ pl = A.gc + (size_t)c * A.cstride;
     const float* __restrict__ pr = A.gc + (size_t)(3 + c) * A.cstride;
     const float* __restrict__ po = A.oc + (size_t)c * A.cstride;
@@ -781,7 +801,46 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
         }
         cp_async_commit();               // an empty group past the end keeps the group count uniform
     };
-    if (INTERIOR) {
+    // the same request as TMA row segments (lane 0 only); fx0 / a0: first fine / coarse column of the warp's tile
+    const int fx0 = fx - 4 * lane, a0 = fx0 >> 1;
+    auto issue_bulk = [&](int k) {
+        if (k < CL_R) {
+            CollapseBulkStage& S = ring->st[k % CL_STAGES];
+            unsigned long long* bar = &ring->bar[k % CL_STAGES];
+            mbar_expect_tx(bar, CL_BULK_BYTES);
+            const size_t coff = (size_t)(cy0 + k + 1) * A.cpitch + a0 - 4;
+            bulk_g2s(S.coarse[0], pl + coff, 288, bar);
+            bulk_g2s(S.coarse[1], pr + coff, 288, bar);
+            bulk_g2s(S.coarse[2], po + coff, 288, bar);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int fy = 2 * (cy0 + k) + r;
+                if (L0) {
+                    const size_t o = (size_t)fy * A.wpitch + fx0;
+                    bulk_g2s(S.fine[3 * r + 0], A.w1 + o, 512, bar);
+                    bulk_g2s(S.fine[3 * r + 1], A.w2 + o, 512, bar);
+                    bulk_g2s(S.fine[3 * r + 2], A.mask0 + (size_t)fy * A.mpitch + fx0, 512, bar);
+                } else {
+                    const float* __restrict__ gp = A.gfine + (size_t)fy * A.fpitch + fx0;
+                    bulk_g2s(S.fine[3 * r + 0], gp + (size_t)c * A.fstride, 512, bar);
+                    bulk_g2s(S.fine[3 * r + 1], gp + (size_t)(3 + c) * A.fstride, 512, bar);
+                    bulk_g2s(S.fine[3 * r + 2], gp + (size_t)6 * A.fstride, 512, bar);
+                }
+            }
+        }
+    };
+    if (INTERIOR && BULK) {
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < CL_STAGES; ++k) mbar_init(&ring->bar[k], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < CL_STAGES; ++k) issue_bulk(k);
+        }
+        __syncwarp();
+        coarse_now(cy0 - 1, hm);
+        coarse_now(cy0, h0);
+    } else if (INTERIOR) {
 #pragma unroll
         for (int k = 0; k < CL_STAGES; ++k) issue(k);
         coarse_now(cy0 - 1, hm);
@@ -798,7 +857,28 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
         if (!INTERIOR && fy >= A.h) break;
         const bool two = INTERIOR || fy + 1 < A.h;
         float gl[2][4], gr[2][4], mk[2][4];
-        if (INTERIOR) {
+        if (INTERIOR && BULK) {
+            mbar_wait(&ring->bar[k % CL_STAGES], (unsigned)(k / CL_STAGES) & 1u);
+            const CollapseBulkStage& S = ring->st[k % CL_STAGES];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                UpRaw u;
+                const float* seg = S.coarse[p] + 4 + 2 * lane;          // coarse column a = a0 + 2 * lane
+                u.cm = seg[-1]; u.c01 = *reinterpret_cast<const float2*>(seg); u.cp = seg[2];
+                up_row_raw(u, hp[p]);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                FineRaw<L0> rf;
+                fine_from_rows(reinterpret_cast<const float4*>(S.fine[3 * r + 0])[lane], reinterpret_cast<const float4*>(S.fine[3 * r + 1])[lane],
+                               reinterpret_cast<const float4*>(S.fine[3 * r + 2])[lane], rf);
+                fine_unpack(rf, c, gl[r], gr[r], mk[r]);
+            }
+            // the stage is in registers: hand it back to the TMA (cross-proxy fence: generic reads before async writes)
+            __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            if (lane == 0) issue_bulk(k + CL_STAGES);
+        } else if (INTERIOR) {
             cp_async_wait<CL_STAGES - 1>();
             const CollapseStage& S = stages[k % CL_STAGES];
 #pragma unroll
@@ -835,7 +915,7 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
         *reinterpret_cast<float4*>(orow) = make_float4(e[0], e[1], e[2], e[3]);
         if (two) *reinterpret_cast<float4*>(orow + A.opitch) = make_float4(o[0], o[1], o[2], o[3]);
         orow += 2 * (size_t)A.opitch;
-        if (INTERIOR) issue(k + CL_STAGES);           // the slot just consumed is free again
+        if (INTERIOR && !BULK) issue(k + CL_STAGES);  // the slot just consumed is free again
 #pragma unroll
         for (int p = 0; p < 3; ++p)
 #pragma unroll
@@ -853,8 +933,8 @@ __global__ void __launch_bounds__(96, 8)
 k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride, const float* __restrict__ mask0, int mpitch,
                 size_t m0stride, const float* __restrict__ g_fine, int w, int h, int fpitch, size_t fstride,
                 const float* __restrict__ g_coarse, const float* __restrict__ out_coarse, int cw, int ch, int cpitch,
-                size_t cstride, float* __restrict__ out_fine, int opitch, size_t ostride) {
-    extern __shared__ __align__(16) unsigned char smem_dyn[];
+                size_t cstride, float* __restrict__ out_fine, int opitch, size_t ostride, int use_bulk) {
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
     CollapseStage* stages = reinterpret_cast<CollapseStage*>(smem_dyn) + CL_STAGES * threadIdx.y;
     const int f = blockIdx.z, c = threadIdx.y;
     const int fx = blockIdx.x * 128 + 4 * threadIdx.x, cy0 = blockIdx.y * CL_R;
@@ -868,8 +948,18 @@ k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride,
     const int a = fx >> 1;
     const bool lane_in = a >= 1 && a + 2 <= cw - 1;                       // implies fx + 3 < w
     const bool rows_in = cy0 >= 1 && cy0 + CL_R <= ch - 1 && 2 * (cy0 + CL_R) <= h;
-    if (__all_sync(FULL, lane_in && rows_in)) collapse_body<L0, true>(A, c, fx, cy0, stages, threadIdx.x);
-    else if (fx < w) collapse_body<L0, false>(A, c, fx, cy0, stages, threadIdx.x);
+    if (__all_sync(FULL, lane_in && rows_in)) {
+        // TMA staging where the tile's 72-column coarse segment and 128-column fine segments lie inside their rows
+        const int a0 = blockIdx.x * 64;
+        const bool bulk_ok = use_bulk && a0 - 4 >= 0 && a0 + 68 <= cpitch && (int)blockIdx.x * 128 + 128 <= (L0 ? wpitch : fpitch) &&
+                             (!L0 || (int)blockIdx.x * 128 + 128 <= mpitch);
+        if (bulk_ok)
+            collapse_body<L0, true, true>(A, c, fx, cy0, stages, threadIdx.x, reinterpret_cast<CollapseBulkRing*>(smem_dyn) + threadIdx.y);
+        else
+            collapse_body<L0, true>(A, c, fx, cy0, stages, threadIdx.x);
+    } else if (fx < w) {
+        collapse_body<L0, false>(A, c, fx, cy0, stages, threadIdx.x);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -877,6 +967,12 @@ k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride,
 static bool use_bulk() {
     static const bool v = [] { const char* e = std::getenv("POPPY_CUDA_NO_BULK"); return !(e && e[0] == '1'); }();
     return v;
+}
+
+// A/B switch: POPPY_CUDA_COLLAPSE_BULK bit 0 = level-0 collapse, bit 1 = the other levels (default 3: both use TMA staging)
+static int collapse_bulk_mode() {
+    static const int v = [] { const char* e = std::getenv("POPPY_CUDA_COLLAPSE_BULK"); return e ? std::atoi(e) : 3; }();
+    return use_bulk() ? v : 0;
 }
 
 void launch_pyr_down0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* basis, int bpitch,
@@ -915,7 +1011,7 @@ void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const f
     }
     k_collapse_roll<false><<<dim3(div_up(fl.w, 128), div_up(fl.h, 2 * CL_R), frames), dim3(32, 3), CL_SMEM, st>>>(
         nullptr, 0, 0, nullptr, 0, 0, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
-        cl.plane_stride, out_fine, fl.pitch, fl.plane_stride);
+        cl.plane_stride, out_fine, fl.pitch, fl.plane_stride, collapse_bulk_mode() & 2 ? 1 : 0);
 }
 
 void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
@@ -928,7 +1024,7 @@ void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_
     }
     k_collapse_roll<true><<<dim3(div_up(w, 128), div_up(h, 2 * CL_R), frames), dim3(32, 3), CL_SMEM, st>>>(
         warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
-        cl.plane_stride, out_fine, ol.pitch, ol.plane_stride);
+        cl.plane_stride, out_fine, ol.pitch, ol.plane_stride, collapse_bulk_mode() & 1 ? 1 : 0);
 }
 
 }  // namespace poppy
