@@ -667,9 +667,13 @@ struct __align__(128) CollapseBulkStage {
     float fine[6][128];                    // rows fy, fy+1: (image 1 | left, image 2 | right, mask) x 2; [3 * r + i]
     float coarse[3][72];                   // coarse row sy+1 of (left, right, out): columns a0 - 4 .. a0 + 67
 };
+#ifndef POPPY_CL_BULK_STAGES
+#define POPPY_CL_BULK_STAGES 2
+#endif
+constexpr int CL_BULK_STAGES = POPPY_CL_BULK_STAGES;
 struct __align__(128) CollapseBulkRing {   // one per warp
-    CollapseBulkStage st[CL_STAGES];
-    unsigned long long bar[CL_STAGES];
+    CollapseBulkStage st[CL_BULK_STAGES];
+    unsigned long long bar[CL_BULK_STAGES];
 };
 constexpr unsigned CL_BULK_BYTES = 6 * 512 + 3 * 288;
 constexpr size_t CL_SMEM_LDGSTS = sizeof(CollapseStage) * CL_STAGES * 3, CL_SMEM_BULK = sizeof(CollapseBulkRing) * 3;
@@ -805,8 +809,8 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
     const int fx0 = fx - 4 * lane, a0 = fx0 >> 1;
     auto issue_bulk = [&](int k) {
         if (k < CL_R) {
-            CollapseBulkStage& S = ring->st[k % CL_STAGES];
-            unsigned long long* bar = &ring->bar[k % CL_STAGES];
+            CollapseBulkStage& S = ring->st[k % CL_BULK_STAGES];
+            unsigned long long* bar = &ring->bar[k % CL_BULK_STAGES];
             mbar_expect_tx(bar, CL_BULK_BYTES);
             const size_t coff = (size_t)(cy0 + k + 1) * A.cpitch + a0 - 4;
             bulk_g2s(S.coarse[0], pl + coff, 288, bar);
@@ -832,10 +836,10 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
     if (INTERIOR && BULK) {
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < CL_STAGES; ++k) mbar_init(&ring->bar[k], 1);
+            for (int k = 0; k < CL_BULK_STAGES; ++k) mbar_init(&ring->bar[k], 1);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 #pragma unroll
-            for (int k = 0; k < CL_STAGES; ++k) issue_bulk(k);
+            for (int k = 0; k < CL_BULK_STAGES; ++k) issue_bulk(k);
         }
         __syncwarp();
         coarse_now(cy0 - 1, hm);
@@ -858,8 +862,8 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
         const bool two = INTERIOR || fy + 1 < A.h;
         float gl[2][4], gr[2][4], mk[2][4];
         if (INTERIOR && BULK) {
-            mbar_wait(&ring->bar[k % CL_STAGES], (unsigned)(k / CL_STAGES) & 1u);
-            const CollapseBulkStage& S = ring->st[k % CL_STAGES];
+            mbar_wait(&ring->bar[k % CL_BULK_STAGES], (unsigned)(k / CL_BULK_STAGES) & 1u);
+            const CollapseBulkStage& S = ring->st[k % CL_BULK_STAGES];
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
                 UpRaw u;
@@ -877,7 +881,7 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
             // the stage is in registers: hand it back to the TMA (cross-proxy fence: generic reads before async writes)
             __syncwarp();
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            if (lane == 0) issue_bulk(k + CL_STAGES);
+            if (lane == 0) issue_bulk(k + CL_BULK_STAGES);
         } else if (INTERIOR) {
             cp_async_wait<CL_STAGES - 1>();
             const CollapseStage& S = stages[k % CL_STAGES];
