@@ -391,15 +391,17 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    // try_wait with a suspend-time hint: a warp whose stage has not landed yet is parked by the hardware instead of
+    // spinning through the issue slots of the warps that have work
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "POPPY_MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra POPPY_MBAR_DONE;\n"
         "bra POPPY_MBAR_WAIT;\n"
         "POPPY_MBAR_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // global -> shared bulk copy (bytes: multiple of 16; both addresses 16-byte aligned), completion on `bar`
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
