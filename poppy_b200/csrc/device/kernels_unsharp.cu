@@ -36,6 +36,7 @@ constexpr int US_W = 120;            // output columns per strip
 constexpr int US_CW = 128;           // computed columns x0-4 .. x0+123
 constexpr int US_XW = 136;           // staged input columns x0-8 .. x0+127
 constexpr int US_STEP = 8;           // rows per step
+constexpr int US_PF_ROWS = US_STEP;  // L2 prefetch distance of the row stage (one step; two bring nothing more)
 constexpr int US_RING = 16;          // ring depth (rows) of the three shared-memory rings
 constexpr int US_CHUNK = 216;        // rows per CTA
 constexpr size_t US_SMEM = ((size_t)US_RING * 3 * US_XW + 2 * (size_t)US_RING * 3 * US_CW) * sizeof(float) +
@@ -118,6 +119,14 @@ template <bool INTERIOR>
 __device__ __forceinline__ void us_row_pass(const UsThread& T, const float* __restrict__ img, int pitch, size_t stride,
                                             float* xs_row, float* rp_row, int v) {
     const float* __restrict__ row = img + (size_t)reflect101(v, T.h) * pitch + T.gx0;
+    if (INTERIOR) {
+        // the row this warp stages in the NEXT step (8 rows down): start it on its way from HBM to L2 now, so that the
+        // loads below - whose latency nothing in this warp can cover - find it there (shared memory leaves no L1 to
+        // prefetch into)
+        const float* __restrict__ nxt = img + (size_t)reflect101(v + US_PF_ROWS, T.h) * pitch + T.gx0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + c * stride));
+    }
     float4 own[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
