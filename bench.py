@@ -101,6 +101,18 @@ def dominant_kernel_roofline(kern, W, H, F, chunk_frames, peak, traffic, levels=
     return out
 
 
+def issue_roofline(traffic, fps_per_gpu, clocks, sms=148, slots_per_sm=4):
+    """The other roofline of this path: warp instructions per frame (ncu smsp__inst_executed.sum of every kernel,
+    profiles/ncu_traffic.json) against the issue slots of the GPU at the SM clock sampled during the run."""
+    if not traffic or "warp_instructions_per_frame" not in traffic:
+        return None
+    wi = float(sum(traffic["warp_instructions_per_frame"].values()))
+    mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+    peak = sms * slots_per_sm * mhz * 1e6
+    return {"warp_instructions_per_frame": int(wi), "peak_warp_instructions_per_s": peak,
+            "roofline_frames_per_s": peak / wi, "frac": fps_per_gpu * wi / peak}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -412,6 +424,7 @@ def main():
                          "traffic": (int(sum(traffic["bytes_per_frame"].values()) * F) if traffic else None),
                          "traffic_what": "ncu dram__bytes_read+write of all kernels of one step (profiles/ncu_traffic.json)",
                          "dominant_kernel": dominant_kernel_roofline(kern, W, H, F, chunk_used, peak, traffic, L),
+                         "issue": issue_roofline(traffic, fps / world, clocks),
                          "peak_source": peak_src,
                          "scope": "whole render path per GPU (SURVEY.md 8(d) algorithmic bytes/frame x frames/s)",
                          "algorithmic_bytes_per_frame": alg, "kernels": kern,

@@ -41,3 +41,12 @@ def test_committed_traffic_file_is_well_formed():
     assert set(t["bytes_per_frame"]) >= {"raster_warp", "pyr_down", "blend_collapse", "unsharp_store"}
     total = sum(t["bytes_per_frame"].values())
     assert 555_588_480 < total < 2 * 555_588_480          # above the algorithmic model, well under 2x
+
+
+def test_issue_roofline_object():
+    b = _bench()
+    t = b.ncu_traffic()
+    r = b.issue_roofline(t, 3000.0, {"sm_mhz": 1965.0})
+    assert r["warp_instructions_per_frame"] == sum(t["warp_instructions_per_frame"].values())
+    assert abs(r["roofline_frames_per_s"] * r["frac"] - 3000.0) < 1e-6
+    assert 0.3 < r["frac"] < 1.0

@@ -89,6 +89,7 @@ def traffic(path, frames):
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     agg = {}
+    inst = {}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for r in rows[2:]:
         d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
@@ -98,8 +99,10 @@ def traffic(path, frames):
             continue
         b = sum(float(d[k].replace(",", "")) * scale[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         agg[cls] = agg.get(cls, 0.0) + b / frames
+        inst[cls] = inst.get(cls, 0.0) + float(d["smsp__inst_executed.sum"].replace(",", "")) / frames
     print(json.dumps({"source": f"ncu --set full --clock-control none, one {frames}-frame chunk ({path})",
-                      "bytes_per_frame": {k: round(v) for k, v in agg.items()}}, indent=1))
+                      "bytes_per_frame": {k: round(v) for k, v in agg.items()},
+                      "warp_instructions_per_frame": {k: round(v) for k, v in inst.items()}}, indent=1))
 
 
 if __name__ == "__main__":
