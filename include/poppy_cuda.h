@@ -67,6 +67,13 @@ int poppy_cuda_get_info(const poppy_cuda_ctx* ctx, int* width, int* height, int*
 int poppy_cuda_set_keep_stages(poppy_cuda_ctx* ctx, int keep);       /* 1: chunk size 1, stage buffers readable */
 int poppy_cuda_set_chunk_frames(poppy_cuda_ctx* ctx, int frames);    /* frames rendered per kernel batch (>=1) */
 int poppy_cuda_set_stage_timing(poppy_cuda_ctx* ctx, int enable);    /* CUDA-event timing per kernel class */
+/* unsharp_mask stage (reference src/util.cpp:113-148, called at src/algo.cpp:263-264). mode 0 (default): the level-0
+ * collapse stores the 8-bit frame itself, and the exact GaussianBlur + medianBlur + threshold path runs only on the strip
+ * chunks where the range of lapBlend over a pixel's 11x11 footprint could let |x - blur| reach the 0.3 norm threshold;
+ * everywhere else unsharp_mask() provably returns x. mode 1: the exact path on every pixel. Both are bit-identical. */
+int poppy_cuda_set_unsharp_mode(poppy_cuda_ctx* ctx, int mode);
+/* Strip chunks (120 columns x 24 rows) that took the exact unsharp path / all chunks, since the last call; syncs. */
+int poppy_cuda_unsharp_stats(poppy_cuda_ctx* ctx, uint64_t* chunks_exact, uint64_t* chunks_total);
 /* Capacity (entries per frame) of the per-tile triangle lists that feed the rasteriser. The default suits any
  * Delaunay mesh; a frame whose lists do not fit is still rendered exactly (every tile then tests every triangle of
  * that frame), only slower. Exposed so that this path can be exercised by the tests. */

@@ -1,9 +1,25 @@
 // Host-callable launchers of the device kernels (one per kernel class). All launches go to the given stream.
 #pragma once
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace poppy {
+
+// Opt-in to > 48 KB of dynamic shared memory, once per device and kernel: cudaFuncSetAttribute applies to the current
+// device only, and one process may hold contexts on several GPUs (poppy_cuda.h: one context per GPU, thread-safe).
+struct SmemAttrOnce { std::atomic<bool> done[64]; };
+template <class K>
+inline void ensure_smem_attr(K kernel, size_t bytes, SmemAttrOnce& once) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool tracked = dev >= 0 && dev < 64;
+    if (!tracked || !once.done[dev].load(std::memory_order_acquire)) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (tracked) once.done[dev].store(true, std::memory_order_release);
+    }
+}
 
 // ---- kernels_geometry.cu -----------------------------------------------------------------------------------------
 void launch_clip_points(cudaStream_t st, const float2* in, float2* out, int n, int cols, int rows);
@@ -49,14 +65,37 @@ void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* 
 void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
                      LevelDesc cl, float* out_fine, int frames);
 // same for level 0, whose Gaussian level is the warped 8-bit pair + the level-0 mask planes
+// tile_flags (nullable): per frame and 128x32 tile, 0 = the tile is not needed (calm, see below)
 void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
                       size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
-                      float* out_fine, LevelDesc ol, int frames);
+                      float* out_fine, LevelDesc ol, int frames, const unsigned char* tile_flags);
+// level-0 collapse fused with convertTo(CV_8U, 255): stores cvRound(255 out[0]) into the frame ring (exactly the frame
+// wherever unsharp_mask() leaves the pixel untouched) and, per 4x8-pixel block and channel, whether out[0] left [0, 1] by
+// more than 0.001 there: ex[(f*3 + c) * ex_stride + by * ex_pitch + bx]
+void launch_collapse0_emit(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
+                           size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
+                           const FrameParams* fp, uint8_t* frames_base, size_t frame_bytes, unsigned char* ex, int ex_pitch,
+                           size_t ex_stride, int frames);
 
 // ---- kernels_unsharp.cu ------------------------------------------------------------------------------------------
 // unsharp_mask(lapBlend, 1, amount, 0.3) + convertTo(CV_8U, 255)   (reference src/algo.cpp:263-265, util.cpp:113-148)
+// chunk_rows: rows per CTA (multiple of 8); chunk_flags (nullable): per frame and (strip, chunk), 0 = skip
 void launch_unsharp_store(cudaStream_t st, const float* lap_blend, LevelDesc l, const FrameParams* fp,
-                          uint8_t* frames_base, size_t frame_bytes, int frames);
+                          uint8_t* frames_base, size_t frame_bytes, int frames, int chunk_rows,
+                          const unsigned char* chunk_flags);
+// Calm analysis between the fused level-0 collapse and the exact unsharp path (see EmitCtx, kernels_pyramid.cu): bounds
+// |x - GaussianBlur(x)| from the second differences of the stored frame bytes and the clamp-excess flags. Outputs (per
+// frame): block_dev [ceil(h/8)][ceil(w/4)][2] the per-block deviation maxima (scratch), block_flags [ceil(h/8)][ceil(w/4)] = 1
+// where a 4x8 block fails the bound, chunk_flags
+// [ceil(h/chunk_rows)][ceil(w/120)] = 1 where a strip chunk of launch_unsharp_store holds a pixel that unsharp_mask() may
+// change, tile_flags [ceil(h/32)][ceil(w/128)] = 1 where a level-0 collapse tile is read by such a chunk; counts[f] =
+// flagged chunks of frame f, *total += all of them (statistics). force_all: flag everything (exact path everywhere).
+void launch_calm_analysis(cudaStream_t st, const uint8_t* frames_base, size_t frame_bytes, const FrameParams* fp,
+                          const unsigned char* ex, int ex_pitch, size_t ex_stride, int w, int h, int frames, int chunk_rows,
+                          unsigned char* block_dev, unsigned char* block_flags, unsigned char* chunk_flags,
+                          unsigned char* tile_flags, int* counts, unsigned long long* total, int force_all);
+constexpr int UNSHARP_STRIP_W = 120;       // output columns per strip of launch_unsharp_store
+constexpr int CALM_BLOCK_W = 4, CALM_BLOCK_H = 8;
 // order-dependent checksum of a byte range
 void launch_checksum(cudaStream_t st, const uint8_t* data, size_t bytes, unsigned long long* out);
 

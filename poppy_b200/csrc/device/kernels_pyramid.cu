@@ -763,10 +763,74 @@ __device__ __forceinline__ void fine_from_stage(const CollapseStage& S, int r, i
     f.l = S.fine[3 * r + 0][lane]; f.r = S.fine[3 * r + 1][lane]; f.m = S.fine[3 * r + 2][lane];
 }
 
+// ---- fused 8-bit store of the level-0 collapse ("calm" route of the unsharp stage) -------------------------------------
+// unsharp_mask() leaves a pixel untouched unless the 3x3 median of d = x - GaussianBlur(x, sigma 1) reaches norm 0.3
+// (src/util.cpp:135-145). With the symmetric 9-tap kernel, d = (I - Bx) x + Bx (I - By) x and
+//     (I - Bx) x (p) = - sum_{a>0} w_a [x(p+a) + x(p-a) - 2 x(p)],   |x(p+a) + x(p-a) - 2 x(p)| <= a^2 max |d2x|,
+// so |d| <= 0.5 (max |d2x| + max |d2y|) over the pixel's footprint (sum_{a>0} w_a a^2 = 0.49996), d2 being the unit second
+// differences of x (reflected at the image border like the blur). Where that bound stays below 0.1732 in every channel no
+// median can reach the threshold (3 * 0.1732^2 < 0.09) and the frame pixel is exactly cvRound(255 x): neither blur nor
+// median have to be evaluated. The level-0 collapse therefore stores the 8-bit frame itself; k_calm_scan
+// (kernels_unsharp.cu) bounds the second differences from the stored bytes (|x - byte/255| <= 0.5/255 unless x was clamped,
+// which this kernel records per 4x8 block as `excess`), and only the strip chunks that fail the bound run the exact blur +
+// median path, which overwrites them (k_collapse_roll<true, false> + k_unsharp_strip on the flagged tiles).
+constexpr float EMIT_EXCESS_TOL = 0.255f;      // |255 x - clamp(255 x)| tolerated in a calm block (0.001 in units of x)
+struct EmitCtx {
+    uint8_t* frame;            // ring slot of the frame: tight rows of 3 * w bytes
+    unsigned char* ex;         // clamp-excess flags of this frame and channel: [ceil(h/8)][ex_pitch] blocks of 4x8 pixels
+    int ex_pitch;
+    unsigned char* rowbuf;     // shared: [2 step parities][2 rows][384 bytes] interleaved BGR of the CTA's 128 columns
+    float excess;              // max |255 x - clamp(255 x)| of the lane's current block
+};
+
+// cvRound(255 v) saturated to 8 bits as u8_magic() computes it (byte in the low mantissa bits), also tracking how far v
+// lies outside [0, 1]
+__device__ __forceinline__ float emit_u8(EmitCtx& E, float v) {
+    const float t = __fmul_rn(v, 255.f);
+    const float cl = fminf(fmaxf(t, 0.f), 255.f);
+    E.excess = fmaxf(E.excess, fabsf(__fsub_rn(t, cl)));
+    return __fadd_rn(cl, 12582912.0f);
+}
+__device__ __forceinline__ void emit_flush(EmitCtx& E, int fy, int fx) {
+    E.ex[(size_t)(fy / CALM_BLOCK_H) * E.ex_pitch + fx / CALM_BLOCK_W] = E.excess > EMIT_EXCESS_TOL ? 1 : 0;
+    E.excess = 0.f;
+}
+// INTERIOR tiles (all 96 threads of the CTA in step, w % 4 == 0): the three channel warps interleave their bytes in
+// shared memory and every warp stores one contiguous 128-byte third of each 384-byte frame row segment
+__device__ __forceinline__ void emit_rows_interior(EmitCtx& E, int k, const float (&e)[4], const float (&o)[4], int c, int lane,
+                                                   int w, int fy, int fx0) {
+    unsigned char* b = E.rowbuf + (k & 1) * 768;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        b[12 * lane + 3 * i + c] = (unsigned char)(__float_as_uint(emit_u8(E, e[i])) & 255u);
+        b[384 + 12 * lane + 3 * i + c] = (unsigned char)(__float_as_uint(emit_u8(E, o[i])) & 255u);
+    }
+    __syncthreads();            // one barrier per step: the buffers alternate with the step parity
+    const uint32_t* bw = reinterpret_cast<const uint32_t*>(b);
+    const uint32_t w0 = bw[32 * c + lane], w1 = bw[96 + 32 * c + lane];
+    uint32_t* drow = reinterpret_cast<uint32_t*>(E.frame + ((size_t)fy * w + fx0) * 3) + 32 * c + lane;
+    drow[0] = w0;
+    drow[(size_t)w * 3 / 4] = w1;
+    if ((k & 3) == 3) emit_flush(E, fy, fx0 + 4 * lane);
+}
+// any tile, any lane subset: every lane stores the bytes of its own channel
+__device__ __forceinline__ void emit_rows_generic(EmitCtx& E, int k, const float (&e)[4], const float (&o)[4], bool two, int c, int w,
+                                                  int fy, int fx) {
+    const int n = min(4, w - fx);
+    uint8_t* d0 = E.frame + ((size_t)fy * w + fx) * 3 + c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (i < n) {
+            d0[3 * i] = (uint8_t)(__float_as_uint(emit_u8(E, e[i])) & 255u);
+            if (two) d0[(size_t)w * 3 + 3 * i] = (uint8_t)(__float_as_uint(emit_u8(E, o[i])) & 255u);
+        }
+    if ((k & 3) == 3) emit_flush(E, fy, fx);
+}
+
 // One warp = one colour channel c of a 128 x 32 fine tile. `stages`: this warp's CL_STAGES staging slots.
-template <bool L0, bool INTERIOR, bool BULK = false>
+template <bool L0, bool INTERIOR, bool BULK = false, bool EMIT = false>
 __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int fx, int cy0, CollapseStage* stages, int lane,
-                                              CollapseBulkRing* ring = nullptr) {
+                                              CollapseBulkRing* ring = nullptr, EmitCtx* E = nullptr, bool emit_words = false) {
     const float* __restrict__ pl = A.gc + (size_t)c * A.cstride;
     const float* __restrict__ pr = A.gc + (size_t)(3 + c) * A.cstride;
     const float* __restrict__ po = A.oc + (size_t)c * A.cstride;
@@ -856,11 +920,13 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
         coarse_now(cy0 >= 1 ? cy0 - 1 : (A.ch > 1 ? 1 : 0), hm);
         coarse_now(cy0, h0);
     }
-    float* __restrict__ orow = A.out + (size_t)c * A.ostride + (size_t)(2 * cy0) * A.opitch + fx;
+    float* __restrict__ orow = EMIT ? nullptr : A.out + (size_t)c * A.ostride + (size_t)(2 * cy0) * A.opitch + fx;
+    int k_done = 0;
 #pragma unroll 1
     for (int k = 0; k < CL_R; ++k) {
         const int sy = cy0 + k, fy = 2 * sy;
         if (!INTERIOR && fy >= A.h) break;
+        k_done = k + 1;
         const bool two = INTERIOR || fy + 1 < A.h;
         float gl[2][4], gr[2][4], mk[2][4];
         if (INTERIOR && BULK) {
@@ -918,15 +984,22 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
                 o[i] = blend1(gl[1][i], gr[1][i], mk[1][i], up_odd(h0[0][i], hp[0][i]), up_odd(h0[1][i], hp[1][i]),
                               up_odd(h0[2][i], hp[2][i]));
         }
-        *reinterpret_cast<float4*>(orow) = make_float4(e[0], e[1], e[2], e[3]);
-        if (two) *reinterpret_cast<float4*>(orow + A.opitch) = make_float4(o[0], o[1], o[2], o[3]);
-        orow += 2 * (size_t)A.opitch;
+        if (EMIT) {
+            if (INTERIOR && emit_words) emit_rows_interior(*E, k, e, o, c, lane, A.w, fy, fx0);
+            else emit_rows_generic(*E, k, e, o, two, c, A.w, fy, fx);
+        } else {
+            *reinterpret_cast<float4*>(orow) = make_float4(e[0], e[1], e[2], e[3]);
+            if (two) *reinterpret_cast<float4*>(orow + A.opitch) = make_float4(o[0], o[1], o[2], o[3]);
+            orow += 2 * (size_t)A.opitch;
+        }
         if (INTERIOR && !BULK) issue(k + CL_STAGES);  // the slot just consumed is free again
 #pragma unroll
         for (int p = 0; p < 3; ++p)
 #pragma unroll
             for (int i = 0; i < 4; ++i) { hm[p][i] = h0[p][i]; h0[p][i] = hp[p][i]; }
     }
+    // a block of the min/max table cut short by the image's last rows
+    if (EMIT && !INTERIOR && k_done > 0 && (k_done & 3) != 0) emit_flush(*E, 2 * (cy0 + k_done - 1), fx);
 }
 
 }  // namespace
@@ -934,15 +1007,21 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
 // block (32, 3): warp = colour channel; grid (ceil(w/128), ceil(h/32), frames).
 // L0: the fine Gaussian level is the warped 8-bit pair (two word planes per frame, wstride words each) + the level-0
 // mask plane written by k_pyr_down0_roll.
-template <bool L0>
+// EMIT (level 0 only): instead of the float planes of out[0] the kernel stores the 8-bit frame cvRound(255 out[0]) into the
+// frame ring and the per-block clamp-excess flags (see EmitCtx). tile_flags (nullable): per frame and CTA tile, 0 = skip the
+// tile (the exact unsharp path only needs out[0] where k_calm_chunks flagged it).
+template <bool L0, bool EMIT>
 __global__ void __launch_bounds__(96, 8)
 k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride, const float* __restrict__ mask0, int mpitch,
                 size_t m0stride, const float* __restrict__ g_fine, int w, int h, int fpitch, size_t fstride,
                 const float* __restrict__ g_coarse, const float* __restrict__ out_coarse, int cw, int ch, int cpitch,
-                size_t cstride, float* __restrict__ out_fine, int opitch, size_t ostride, int use_bulk) {
+                size_t cstride, float* __restrict__ out_fine, int opitch, size_t ostride, int use_bulk,
+                const unsigned char* __restrict__ tile_flags, const FrameParams* __restrict__ fp, uint8_t* __restrict__ frames_base,
+                size_t frame_bytes, unsigned char* __restrict__ ex, int ex_pitch, size_t ex_stride) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     CollapseStage* stages = reinterpret_cast<CollapseStage*>(smem_dyn) + CL_STAGES * threadIdx.y;
     const int f = blockIdx.z, c = threadIdx.y;
+    if (tile_flags && !tile_flags[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
     const int fx = blockIdx.x * 128 + 4 * threadIdx.x, cy0 = blockIdx.y * CL_R;
     CollapseArgs A;
     A.w1 = L0 ? warped + (size_t)f * 2 * wstride : nullptr; A.w2 = L0 ? A.w1 + wstride : nullptr; A.wpitch = wpitch;
@@ -950,7 +1029,16 @@ k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride,
     A.gfine = L0 ? nullptr : g_fine + (size_t)f * 7 * fstride; A.fpitch = fpitch; A.fstride = fstride;
     A.gc = g_coarse + (size_t)f * 7 * cstride; A.oc = out_coarse + (size_t)f * 3 * cstride;
     A.cw = cw; A.ch = ch; A.cpitch = cpitch; A.cstride = cstride;
-    A.out = out_fine + (size_t)f * 3 * ostride; A.opitch = opitch; A.ostride = ostride; A.w = w; A.h = h;
+    A.out = EMIT ? nullptr : out_fine + (size_t)f * 3 * ostride; A.opitch = opitch; A.ostride = ostride; A.w = w; A.h = h;
+    EmitCtx E;
+    bool emit_words = false;
+    if (EMIT) {
+        E.frame = frames_base + (size_t)fp[f].dst_slot * frame_bytes;
+        E.ex = ex + ((size_t)f * 3 + c) * ex_stride; E.ex_pitch = ex_pitch;
+        E.rowbuf = smem_dyn + CL_SMEM;
+        E.excess = 0.f;
+        emit_words = (w & 3) == 0 && (reinterpret_cast<size_t>(E.frame) & 3) == 0;
+    }
     const int a = fx >> 1;
     const bool lane_in = a >= 1 && a + 2 <= cw - 1;                       // implies fx + 3 < w
     const bool rows_in = cy0 >= 1 && cy0 + CL_R <= ch - 1 && 2 * (cy0 + CL_R) <= h;
@@ -960,11 +1048,12 @@ k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride,
         const bool bulk_ok = use_bulk && a0 - 4 >= 0 && a0 + 68 <= cpitch && (int)blockIdx.x * 128 + 128 <= (L0 ? wpitch : fpitch) &&
                              (!L0 || (int)blockIdx.x * 128 + 128 <= mpitch);
         if (bulk_ok)
-            collapse_body<L0, true, true>(A, c, fx, cy0, stages, threadIdx.x, reinterpret_cast<CollapseBulkRing*>(smem_dyn) + threadIdx.y);
+            collapse_body<L0, true, true, EMIT>(A, c, fx, cy0, stages, threadIdx.x, reinterpret_cast<CollapseBulkRing*>(smem_dyn) + threadIdx.y,
+                                                &E, emit_words);
         else
-            collapse_body<L0, true>(A, c, fx, cy0, stages, threadIdx.x);
+            collapse_body<L0, true, false, EMIT>(A, c, fx, cy0, stages, threadIdx.x, nullptr, &E, emit_words);
     } else if (fx < w) {
-        collapse_body<L0, false>(A, c, fx, cy0, stages, threadIdx.x);
+        collapse_body<L0, false, false, EMIT>(A, c, fx, cy0, stages, threadIdx.x, nullptr, &E, false);
     }
 }
 
@@ -986,11 +1075,8 @@ void launch_pyr_down0(cudaStream_t st, const uint32_t* warped, int wpitch, size_
                       int frames) {
     const dim3 grid(div_up(dl.w, 128), div_up(dl.h, 3 * DN_R), 3 * frames), block(32, 3);
     if (use_bulk()) {
-        static bool once = false;
-        if (!once) {
-            cudaFuncSetAttribute(k_pyr_down0_roll<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D0_SMEM);
-            once = true;
-        }
+        static SmemAttrOnce done;
+        ensure_smem_attr(k_pyr_down0_roll<true>, D0_SMEM, done);
         k_pyr_down0_roll<true><<<grid, block, D0_SMEM, st>>>(warped, wpitch, wstride, basis, bpitch, fp, w, h, mask0, m0stride, dst,
                                                             dl.w, dl.h, dl.pitch, dl.plane_stride);
     } else {
@@ -1008,29 +1094,38 @@ void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* 
     k_blend_coarsest<<<dim3(div_up(l.w * l.h, 256), frames), 256, 0, st>>>(g, l.w, l.h, l.pitch, l.plane_stride, out);
 }
 
+constexpr size_t CL_EMIT_SMEM = CL_SMEM + 2 * 2 * 384;
+
 void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
                      LevelDesc cl, float* out_fine, int frames) {
-    static bool once = false;
-    if (!once) {
-        cudaFuncSetAttribute(k_collapse_roll<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM);
-        once = true;
-    }
-    k_collapse_roll<false><<<dim3(div_up(fl.w, 128), div_up(fl.h, 2 * CL_R), frames), dim3(32, 3), CL_SMEM, st>>>(
+    static SmemAttrOnce done;
+    ensure_smem_attr(k_collapse_roll<false, false>, CL_SMEM, done);
+    k_collapse_roll<false, false><<<dim3(div_up(fl.w, 128), div_up(fl.h, 2 * CL_R), frames), dim3(32, 3), CL_SMEM, st>>>(
         nullptr, 0, 0, nullptr, 0, 0, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
-        cl.plane_stride, out_fine, fl.pitch, fl.plane_stride, collapse_bulk_mode() & 2 ? 1 : 0);
+        cl.plane_stride, out_fine, fl.pitch, fl.plane_stride, collapse_bulk_mode() & 2 ? 1 : 0, nullptr, nullptr, nullptr, 0, nullptr, 0, 0);
 }
 
 void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
                       size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
-                      float* out_fine, LevelDesc ol, int frames) {
-    static bool once = false;
-    if (!once) {
-        cudaFuncSetAttribute(k_collapse_roll<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM);
-        once = true;
-    }
-    k_collapse_roll<true><<<dim3(div_up(w, 128), div_up(h, 2 * CL_R), frames), dim3(32, 3), CL_SMEM, st>>>(
+                      float* out_fine, LevelDesc ol, int frames, const unsigned char* tile_flags) {
+    static SmemAttrOnce done;
+    ensure_smem_attr(k_collapse_roll<true, false>, CL_SMEM, done);
+    k_collapse_roll<true, false><<<dim3(div_up(w, 128), div_up(h, 2 * CL_R), frames), dim3(32, 3), CL_SMEM, st>>>(
         warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
-        cl.plane_stride, out_fine, ol.pitch, ol.plane_stride, collapse_bulk_mode() & 1 ? 1 : 0);
+        cl.plane_stride, out_fine, ol.pitch, ol.plane_stride, collapse_bulk_mode() & 1 ? 1 : 0, tile_flags, nullptr, nullptr, 0, nullptr,
+        0, 0);
+}
+
+void launch_collapse0_emit(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
+                           size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
+                           const FrameParams* fp, uint8_t* frames_base, size_t frame_bytes, unsigned char* ex, int ex_pitch,
+                           size_t ex_stride, int frames) {
+    static SmemAttrOnce done;
+    ensure_smem_attr(k_collapse_roll<true, true>, CL_EMIT_SMEM, done);
+    k_collapse_roll<true, true><<<dim3(div_up(w, 128), div_up(h, 2 * CL_R), frames), dim3(32, 3), CL_EMIT_SMEM, st>>>(
+        warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
+        cl.plane_stride, nullptr, 0, 0, collapse_bulk_mode() & 1 ? 1 : 0, nullptr, fp, frames_base, frame_bytes, ex, ex_pitch,
+        ex_stride);
 }
 
 }  // namespace poppy

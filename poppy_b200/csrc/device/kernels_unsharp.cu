@@ -38,7 +38,7 @@ constexpr int US_XW = 136;           // staged input columns x0-8 .. x0+127
 constexpr int US_STEP = 8;           // rows per step
 constexpr int US_PF_ROWS = US_STEP;  // L2 prefetch distance of the row stage (one step; two bring nothing more)
 constexpr int US_RING = 16;          // ring depth (rows) of the three shared-memory rings
-constexpr int US_CHUNK = 216;        // rows per CTA
+constexpr int US_CHUNK = 216;        // default rows per CTA (a launch parameter: the sparse pass over flagged chunks uses fewer)
 constexpr size_t US_SMEM = ((size_t)US_RING * 3 * US_XW + 2 * (size_t)US_RING * 3 * US_CW) * sizeof(float) +
                            US_RING * 4 * sizeof(uint32_t);
 constexpr float US_FLAG_T = 0.17f;   // 3 * 0.17^2 = 0.0867 < 0.09: below this no median can reach the threshold
@@ -321,7 +321,8 @@ __device__ __forceinline__ void us_step(const UsThread& T, int s, const float* _
 // norm_thr2: smallest double whose sqrt is >= (double)0.3f.
 __global__ void __launch_bounds__(256, 3)
 k_unsharp_strip(const float* __restrict__ lap, int w, int h, int pitch, size_t stride, const FrameParams* __restrict__ fp,
-                double norm_thr2, uint8_t* __restrict__ frames_base, size_t frame_bytes) {
+                double norm_thr2, uint8_t* __restrict__ frames_base, size_t frame_bytes, int chunk_rows,
+                const unsigned char* __restrict__ chunk_flags) {
     extern __shared__ __align__(16) float smem_dyn[];
     float* xs = smem_dyn;                                        // [US_RING][3][US_XW]  input rows (virtual, reflected)
     float* rp = xs + US_RING * US_XROW;                          // [US_RING][3][US_CW]  row-pass results
@@ -329,9 +330,10 @@ k_unsharp_strip(const float* __restrict__ lap, int w, int h, int pitch, size_t s
     uint32_t* fl = reinterpret_cast<uint32_t*>(df + US_RING * US_CROW);      // [US_RING][4] flagged 4-px groups per diff row, channel
 
     const int f = blockIdx.z;
+    if (chunk_flags && !chunk_flags[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;    // calm chunk
     UsThread T;
     T.w = w; T.h = h;
-    T.x0 = blockIdx.x * US_W; T.Y0 = blockIdx.y * US_CHUNK; T.Y1 = min(T.Y0 + US_CHUNK, h);
+    T.x0 = blockIdx.x * US_W; T.Y0 = blockIdx.y * chunk_rows; T.Y1 = min(T.Y0 + chunk_rows, h);
     T.warp = threadIdx.x >> 5; T.lane = threadIdx.x & 31;
     T.tail_from = 3 * w - (3 * w) % 8;       // first interleaved element handled by the scalar filter loops
     T.gx0 = T.x0 - 4 + 4 * T.lane;           // this lane's 4 computed columns
@@ -386,8 +388,154 @@ __global__ void k_checksum(const uint8_t* __restrict__ data, size_t bytes, unsig
     if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
+// ---- calm analysis (see EmitCtx in kernels_pyramid.cu) ----------------------------------------------------------------
+// k_calm_scan bounds the unit second differences of lapBlend from the frame bytes q the fused collapse stored. Per 4x8
+// block it records hx = max |floor((q[x-1] + q[x+1]) / 2) - q[x]| and hy (the same along y; neighbours reflected at the
+// image border like the blur's BORDER_REFLECT_101). |q[-1] + q[+1] - 2 q[0]| <= 2 h + 1, and |255 x - q| <= 0.5 (+ 0.255
+// where the block's clamp excess is tolerated), so the second differences of x are below (2 h + 3.02) / 255. A pixel is
+// calm when, over the blocks within 2 block columns / 1 block row (8 pixels each way; its median + blur footprint spans 5
+// columns and 4 rows of second differences), max hx + max hy <= CALM_SUM: then
+//     |x - blur| <= 0.49996 ((2 hx + 3.02) + (2 hy + 3.02)) / 255 + rounding (< 1e-5) < 0.1732,
+// and no 3x3 median can reach norm 0.3 (3 * 0.1732^2 < 0.09).
+constexpr int CALM_SUM = 40;
+static_assert(UNSHARP_STRIP_W == US_W, "strip width");
+static_assert((2 * CALM_SUM + 2 * 3.02) / 255.0 * 0.49996 < 0.1731, "calm bound");
+
+// |floor-avg(a, c) - b| of four bytes at once
+__device__ __forceinline__ unsigned calm_dev4(unsigned a, unsigned b, unsigned c) {
+    return __vabsdiffu4((a & c) + (((a ^ c) & 0xFEFEFEFEu) >> 1), b);
+}
+
+// block (32, 4); grid (ceil(w/128), ceil(h/64), frames). Requires w % 4 == 0, w >= 8, h >= 2 (the launcher flags everything
+// otherwise). A lane owns 4 pixels = 3 words of every row and walks 16 rows (two blocks of the table) with a three-row
+// window; the bytes 3 to the left / right of its own come from the neighbouring lanes' words. The running maxima are kept
+// as 16-bit SIMD lanes (even bytes | odd bytes << 8: VIMNMX.U16x2).
+__global__ void __launch_bounds__(128)
+k_calm_scan(const uint8_t* __restrict__ frames_base, size_t frame_bytes, const FrameParams* __restrict__ fp, int w, int h,
+            const unsigned char* __restrict__ ex, int ex_pitch, size_t ex_stride, int bw, int bh,
+            uchar2* __restrict__ block_dev) {
+    const int f = blockIdx.z, lane = threadIdx.x;
+    const int x = blockIdx.x * 128 + 4 * lane, y0 = (blockIdx.y * 4 + threadIdx.y) * 16;
+    if (y0 >= h) return;
+    const bool active = x < w;
+    const int xc = active ? x : w - 4;                        // inactive lanes shadow the last pixel group
+    const uint8_t* __restrict__ frame = frames_base + (size_t)fp[f].dst_slot * frame_bytes;
+    const size_t row_bytes = (size_t)w * 3;
+    auto load = [&](int y, unsigned (&wd)[5]) {
+        y = y < 0 ? -y : (y >= h ? 2 * h - 2 - y : y);       // BORDER_REFLECT_101
+        const unsigned* __restrict__ p = reinterpret_cast<const unsigned*>(frame + (size_t)y * row_bytes + (size_t)xc * 3);
+        wd[1] = __ldg(p); wd[2] = __ldg(p + 1); wd[3] = __ldg(p + 2);
+        unsigned l = __shfl_up_sync(0xffffffffu, wd[3], 1), r = __shfl_down_sync(0xffffffffu, wd[1], 1);
+        if (lane == 0) l = xc > 0 ? __ldg(p - 1) : __byte_perm(wd[1], wd[2], 0x5433);            // pixel -1 = pixel 1
+        if (lane == 31 || xc + 4 >= w) r = xc + 4 < w ? __ldg(p + 3) : __byte_perm(wd[2], wd[3], 0x4432);   // pixel w = pixel w-2
+        wd[0] = l; wd[4] = r;
+    };
+    unsigned up[5], mid[5], dn[5];
+    load(y0 - 1, up);
+    load(y0, mid);
+    unsigned mx_lo = 0, mx_hi = 0, my_lo = 0, my_hi = 0;
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {
+        const int y = y0 + k;
+        if (y >= h) break;
+        load(y + 1, dn);
+        unsigned vx[3], vy[3];
+#pragma unroll
+        for (int j = 1; j <= 3; ++j) {
+            vx[j - 1] = calm_dev4(__byte_perm(mid[j - 1], mid[j], 0x4321), mid[j], __byte_perm(mid[j], mid[j + 1], 0x6543));
+            vy[j - 1] = calm_dev4(up[j], mid[j], dn[j]);
+        }
+        mx_lo = __vimax3_u16x2(mx_lo, vx[0] & 0x00FF00FFu, vx[1] & 0x00FF00FFu);
+        mx_hi = __vimax3_u16x2(mx_hi, vx[0] & 0xFF00FF00u, vx[1] & 0xFF00FF00u);
+        mx_lo = __vmaxu2(mx_lo, vx[2] & 0x00FF00FFu);
+        mx_hi = __vmaxu2(mx_hi, vx[2] & 0xFF00FF00u);
+        my_lo = __vimax3_u16x2(my_lo, vy[0] & 0x00FF00FFu, vy[1] & 0x00FF00FFu);
+        my_hi = __vimax3_u16x2(my_hi, vy[0] & 0xFF00FF00u, vy[1] & 0xFF00FF00u);
+        my_lo = __vmaxu2(my_lo, vy[2] & 0x00FF00FFu);
+        my_hi = __vmaxu2(my_hi, vy[2] & 0xFF00FF00u);
+        if ((k & 7) == 7 || y == h - 1) {
+            if (active) {
+                const int by = y / CALM_BLOCK_H, bx = x / CALM_BLOCK_W;
+                const unsigned char* __restrict__ e = ex + (size_t)f * 3 * ex_stride + (size_t)by * ex_pitch + bx;
+                unsigned hx = max(max(mx_lo & 0xFFFFu, mx_lo >> 16), max(mx_hi & 0xFFFFu, mx_hi >> 16) >> 8);
+                unsigned hy = max(max(my_lo & 0xFFFFu, my_lo >> 16), max(my_hi & 0xFFFFu, my_hi >> 16) >> 8);
+                if (e[0] || e[ex_stride] || e[2 * ex_stride]) hx = hy = 255u;      // out[0] left [0, 1]: its bytes say nothing
+                block_dev[((size_t)f * bh + by) * bw + bx] = make_uchar2((unsigned char)hx, (unsigned char)hy);
+            }
+            mx_lo = mx_hi = my_lo = my_hi = 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { up[j] = mid[j]; mid[j] = dn[j]; }
+    }
+}
+
+// one thread per block: flagged when max hx + max hy over the blocks within 2 columns / 1 row exceeds CALM_SUM.
+// grid (ceil(bw/128), bh, frames), block 128.
+__global__ void k_calm_blocks(const uchar2* __restrict__ block_dev, int bw, int bh, unsigned char* __restrict__ block_flags) {
+    const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y, f = blockIdx.z;
+    if (bx >= bw) return;
+    const uchar2* __restrict__ t = block_dev + (size_t)f * bh * bw;
+    int hx = 0, hy = 0;
+    for (int y = max(by - 1, 0); y <= min(by + 1, bh - 1); ++y)
+        for (int x = max(bx - 2, 0); x <= min(bx + 2, bw - 1); ++x) {
+            const uchar2 v = t[(size_t)y * bw + x];
+            hx = max(hx, (int)v.x); hy = max(hy, (int)v.y);
+        }
+    block_flags[((size_t)f * bh + by) * bw + bx] = hx + hy > CALM_SUM ? 1 : 0;
+}
+
+// one warp per strip chunk of k_unsharp_strip: flagged when one of its blocks is; a flagged chunk also flags the level-0
+// collapse tiles (128x32) its input footprint touches. grid (ceil(chunks/8), 1, frames), block 256.
+__global__ void k_calm_chunks(const unsigned char* __restrict__ block_flags, int bw, int bh, int w, int h, int chunk_rows,
+                              int strips, int chunks_y, unsigned char* __restrict__ chunk_flags, int tiles_x, int tiles_y,
+                              unsigned char* __restrict__ tile_flags, int* __restrict__ counts,
+                              unsigned long long* __restrict__ total, int force_all) {
+    const int chunk = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, f = blockIdx.z;
+    if (chunk >= strips * chunks_y) return;
+    const int sx = chunk % strips, cy = chunk / strips;
+    const int x0 = sx * US_W, x1 = min(x0 + US_W, w), Y0 = cy * chunk_rows, Y1 = min(Y0 + chunk_rows, h);
+    const int bx0 = x0 / CALM_BLOCK_W, bx1 = (x1 - 1) / CALM_BLOCK_W, by0 = Y0 / CALM_BLOCK_H, by1 = (Y1 - 1) / CALM_BLOCK_H;
+    const int nbx = bx1 - bx0 + 1, n = nbx * (by1 - by0 + 1);
+    bool any = force_all != 0;
+    const unsigned char* __restrict__ bf = block_flags + (size_t)f * bh * bw;
+    for (int i = lane; i < n && !any; i += 32) any = bf[(size_t)(by0 + i / nbx) * bw + bx0 + i % nbx] != 0;
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) {
+        chunk_flags[(size_t)f * strips * chunks_y + chunk] = any ? 1 : 0;
+        if (any) { atomicAdd(&counts[f], 1); atomicAdd(total, 1ull); }
+    }
+    if (any) {
+        const int tx0 = max(x0 - 8, 0) / 128, tx1 = (min(x0 + 128, w) - 1) / 128;
+        const int ty0 = max(Y0 - 5, 0) / 32, ty1 = (min(Y1 + 5, h) - 1) / 32;
+        const int ntx = tx1 - tx0 + 1, nt = ntx * (ty1 - ty0 + 1);
+        for (int i = lane; i < nt; i += 32)
+            tile_flags[((size_t)f * tiles_y + ty0 + i / ntx) * tiles_x + tx0 + i % ntx] = 1;
+    }
+}
+
+void launch_calm_analysis(cudaStream_t st, const uint8_t* frames_base, size_t frame_bytes, const FrameParams* fp,
+                          const unsigned char* ex, int ex_pitch, size_t ex_stride, int w, int h, int frames, int chunk_rows,
+                          unsigned char* block_dev, unsigned char* block_flags, unsigned char* chunk_flags,
+                          unsigned char* tile_flags, int* counts, unsigned long long* total, int force_all) {
+    const int bw = div_up(w, CALM_BLOCK_W), bh = div_up(h, CALM_BLOCK_H);
+    const int strips = div_up(w, US_W), chunks_y = div_up(h, chunk_rows), tiles_x = div_up(w, 128), tiles_y = div_up(h, 32);
+    // the byte scan needs word-aligned rows; odd widths and tiny frames take the exact path everywhere
+    if ((w & 3) != 0 || w < 8 || h < 2 || (reinterpret_cast<size_t>(frames_base) & 3) != 0 || (frame_bytes & 3) != 0) force_all = 1;
+    cudaMemsetAsync(tile_flags, 0, (size_t)frames * tiles_x * tiles_y, st);
+    cudaMemsetAsync(counts, 0, (size_t)frames * sizeof(int), st);
+    if (!force_all) {
+        k_calm_scan<<<dim3(div_up(w, 128), div_up(h, 64), frames), dim3(32, 4), 0, st>>>(
+            frames_base, frame_bytes, fp, w, h, ex, ex_pitch, ex_stride, bw, bh, reinterpret_cast<uchar2*>(block_dev));
+        k_calm_blocks<<<dim3(div_up(bw, 128), bh, frames), 128, 0, st>>>(reinterpret_cast<const uchar2*>(block_dev), bw, bh, block_flags);
+    }
+    k_calm_chunks<<<dim3(div_up(strips * chunks_y, 8), 1, frames), 256, 0, st>>>(block_flags, bw, bh, w, h, chunk_rows, strips, chunks_y,
+                                                                                 chunk_flags, tiles_x, tiles_y, tile_flags, counts,
+                                                                                 total, force_all);
+}
+
 void launch_unsharp_store(cudaStream_t st, const float* lap_blend, LevelDesc l, const FrameParams* fp,
-                          uint8_t* frames_base, size_t frame_bytes, int frames) {
+                          uint8_t* frames_base, size_t frame_bytes, int frames, int chunk_rows,
+                          const unsigned char* chunk_flags) {
     // smallest double s with sqrt(s) >= (double)0.3f: lets the kernel compare the squared norm (exactly
     // equivalent to "cv::norm(diff) >= threshold" with a correctly rounded sqrt)
     static const double thr2 = [] {
@@ -397,13 +545,11 @@ void launch_unsharp_store(cudaStream_t st, const float* lap_blend, LevelDesc l, 
         while (__builtin_sqrt(s) < t) s = __builtin_nextafter(s, 1.0);
         return s;
     }();
-    static bool once = false;
-    if (!once) {
-        cudaFuncSetAttribute(k_unsharp_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)US_SMEM);
-        once = true;
-    }
-    k_unsharp_strip<<<dim3(div_up(l.w, US_W), div_up(l.h, US_CHUNK), frames), 256, US_SMEM, st>>>(
-        lap_blend, l.w, l.h, l.pitch, l.plane_stride, fp, thr2, frames_base, frame_bytes);
+    static SmemAttrOnce done;
+    ensure_smem_attr(k_unsharp_strip, US_SMEM, done);
+    if (chunk_rows <= 0) chunk_rows = US_CHUNK;
+    k_unsharp_strip<<<dim3(div_up(l.w, US_W), div_up(l.h, chunk_rows), frames), 256, US_SMEM, st>>>(
+        lap_blend, l.w, l.h, l.pitch, l.plane_stride, fp, thr2, frames_base, frame_bytes, chunk_rows, chunk_flags);
 }
 
 void launch_checksum(cudaStream_t st, const uint8_t* data, size_t bytes, unsigned long long* out) {

@@ -28,11 +28,15 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum KernelClass { KC_POINTS = 0, KC_GEOMETRY, KC_BIN, KC_WARP, KC_PYR_DOWN, KC_COLLAPSE, KC_UNSHARP, KC_MISC, KC_COUNT };
+enum KernelClass { KC_POINTS = 0, KC_GEOMETRY, KC_BIN, KC_WARP, KC_PYR_DOWN, KC_COLLAPSE, KC_CALM, KC_UNSHARP, KC_MISC, KC_COUNT };
 const char* const kClassNames[KC_COUNT] = {"lerp_points", "tri_geometry", "bin_triangles", "raster_warp",
-                                           "pyr_down", "blend_collapse", "unsharp_store", "misc"};
+                                           "pyr_down", "blend_collapse", "calm_analysis", "unsharp_store", "misc"};
 
 struct TimedLaunch { int cls; cudaEvent_t a, b; };
+
+// rows per CTA of the exact unsharp pass over flagged strip chunks (the dense pass used 216; a finer grain keeps calm
+// regions out of the exact path at the price of the 10-row warm-up per chunk)
+constexpr int kSparseChunkRows = 24;
 
 }  // namespace
 
@@ -81,12 +85,23 @@ struct poppy_cuda_ctx {
         int *d_tile_cnt = nullptr, *d_tile_off = nullptr, *d_tile_list = nullptr, *d_overflow = nullptr;
         uint32_t* d_warped = nullptr;        // per frame: remap of image 1, remap of image 2 (packed BGRX words)
         float *d_mask0 = nullptr, *d_g = nullptr, *d_o = nullptr;
+        // calm analysis of the unsharp stage: clamp-excess flags of out[0], block / strip-chunk / collapse-tile flags
+        unsigned char* d_excess = nullptr;
+        unsigned char *d_block_dev = nullptr, *d_block_flags = nullptr, *d_chunk_flags = nullptr, *d_tile_flags = nullptr;
+        int* d_calm_counts = nullptr;
         FrameParams* h_fp = nullptr;         // pinned staging
         int32_t* h_tri = nullptr;
     } lane[4];
     int want_lanes = 3;                      // POPPY_CUDA_LANES (1..4)
     int n_lanes = 0;                         // lanes allocated (0 = none yet)
     int n_tiles = 0, list_cap = 0;
+    // unsharp stage: 0 = the fused level-0 collapse stores the frame and only strip chunks that can reach the unsharp
+    // threshold run the exact blur + median path; 1 = the exact path everywhere (A/B and tests; forced by keep_stages)
+    int unsharp_mode = 0;
+    int mm_pitch = 0;                        // blocks per row of the clamp-excess table, padded
+    size_t mm_stride = 0;
+    unsigned long long* d_calm_total = nullptr;      // flagged strip chunks since the last stats read
+    uint64_t calm_chunks_total = 0;
 
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
@@ -125,6 +140,7 @@ void free_chunk(poppy_cuda_ctx* c) {
         cudaFree(l.d_fp); cudaFree(l.d_tri); cudaFree(l.d_inv); cudaFree(l.d_rast); cudaFree(l.d_trimap);
         cudaFree(l.d_tile_cnt); cudaFree(l.d_tile_off); cudaFree(l.d_tile_list); cudaFree(l.d_overflow);
         cudaFree(l.d_warped); cudaFree(l.d_mask0); cudaFree(l.d_g); cudaFree(l.d_o);
+        cudaFree(l.d_excess); cudaFree(l.d_block_dev); cudaFree(l.d_block_flags); cudaFree(l.d_chunk_flags); cudaFree(l.d_tile_flags); cudaFree(l.d_calm_counts);
         cudaFreeHost(l.h_fp); cudaFreeHost(l.h_tri);
         cudaStream_t st = l.stream; cudaEvent_t e1 = l.ev_staged, e2 = l.ev_done;
         l = poppy_cuda_ctx::Lane();
@@ -169,6 +185,12 @@ int ensure_chunk(poppy_cuda_ctx* c) {
         CU_TRY(c, dmalloc(&l.d_mask0, B * c->padded_pixels()));
         CU_TRY(c, dmalloc(&l.d_g, B * c->g_floats));
         CU_TRY(c, dmalloc(&l.d_o, B * c->o_floats));
+        CU_TRY(c, dmalloc(&l.d_excess, B * 3 * c->mm_stride));
+        CU_TRY(c, dmalloc(&l.d_block_dev, 2 * B * (size_t)div_up(c->w, CALM_BLOCK_W) * div_up(c->h, CALM_BLOCK_H)));
+        CU_TRY(c, dmalloc(&l.d_block_flags, B * (size_t)div_up(c->w, CALM_BLOCK_W) * div_up(c->h, CALM_BLOCK_H)));
+        CU_TRY(c, dmalloc(&l.d_chunk_flags, B * (size_t)div_up(c->w, UNSHARP_STRIP_W) * div_up(c->h, kSparseChunkRows)));
+        CU_TRY(c, dmalloc(&l.d_tile_flags, B * (size_t)div_up(c->w, 128) * div_up(c->h, 32)));
+        CU_TRY(c, dmalloc(&l.d_calm_counts, B));
         CU_TRY(c, cudaMallocHost((void**)&l.h_fp, B * sizeof(FrameParams)));
         CU_TRY(c, cudaMallocHost((void**)&l.h_tri, std::max<size_t>(B * c->max_tri, 1) * 3 * sizeof(int32_t)));
     }
@@ -282,12 +304,26 @@ int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* s
         Scope s(c, KC_COLLAPSE, st);
         launch_collapse(st, g_level(c, ln, k), c->lv[k], g_level(c, ln, k + 1), o_level(c, ln, k + 1), c->lv[k + 1], o_level(c, ln, k), nb);
     }
+    const int force_exact = (c->unsharp_mode == 1 || c->keep_stages) ? 1 : 0;
+    {   Scope s(c, KC_COLLAPSE, st);
+        launch_collapse0_emit(st, ln.d_warped, c->pitch0(), c->padded_pixels(), ln.d_mask0, c->pitch0(), c->padded_pixels(), w, h,
+                              g_level(c, ln, 1), o_level(c, ln, 1), c->lv[1], ln.d_fp, c->d_frames, c->frame_bytes(), ln.d_excess,
+                              c->mm_pitch, c->mm_stride, nb);
+    }
+    {   Scope s(c, KC_CALM, st);
+        c->launches += 2;       // byte scan + block flags + chunk flags
+        launch_calm_analysis(st, c->d_frames, c->frame_bytes(), ln.d_fp, ln.d_excess, c->mm_pitch, c->mm_stride, w, h, nb,
+                             kSparseChunkRows, ln.d_block_dev, ln.d_block_flags, ln.d_chunk_flags, ln.d_tile_flags, ln.d_calm_counts, c->d_calm_total,
+                             force_exact);
+        c->calm_chunks_total += (uint64_t)nb * div_up(w, UNSHARP_STRIP_W) * div_up(h, kSparseChunkRows);
+    }
     {   Scope s(c, KC_COLLAPSE, st);
         launch_collapse0(st, ln.d_warped, c->pitch0(), c->padded_pixels(), ln.d_mask0, c->pitch0(), c->padded_pixels(), w, h, g_level(c, ln, 1),
-                         o_level(c, ln, 1), c->lv[1], o_level(c, ln, 0), c->lv[0], nb);
+                         o_level(c, ln, 1), c->lv[1], o_level(c, ln, 0), c->lv[0], nb, ln.d_tile_flags);
     }
     {   Scope s(c, KC_UNSHARP, st);
-        launch_unsharp_store(st, o_level(c, ln, 0), c->lv[0], ln.d_fp, c->d_frames, c->frame_bytes(), nb);
+        launch_unsharp_store(st, o_level(c, ln, 0), c->lv[0], ln.d_fp, c->d_frames, c->frame_bytes(), nb, kSparseChunkRows,
+                             ln.d_chunk_flags);
     }
     if (chain) {
         Scope s(c, KC_MISC, st);
@@ -368,6 +404,10 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
         const long long want = std::max<long long>(8LL * max_triangles + 4 * tiles, 1LL << 20);
         c->list_cap = (int)std::min<long long>(all, want);
     }
+    c->mm_pitch = (div_up(width, CALM_BLOCK_W) + 15) & ~15;
+    c->mm_stride = (size_t)c->mm_pitch * div_up(height, CALM_BLOCK_H);
+    CR_TRY(dmalloc(&c->d_calm_total, (size_t)1));
+    CR_TRY(cudaMemset(c->d_calm_total, 0, sizeof(unsigned long long)));
     const size_t px = c->pixels();
     CR_TRY(dmalloc(&c->d_src_stage, px));
     for (int i = 0; i < 3; ++i) {
@@ -411,7 +451,7 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
         if (c->a_src[i]) cudaFreeArray(c->a_src[i]);
     }
     cudaFree(c->d_pts1_raw); cudaFree(c->d_pts2_raw); cudaFree(c->d_pts1); cudaFree(c->d_pts2); cudaFree(c->d_morphed);
-    cudaFree(c->d_frames); cudaFree(c->d_sum);
+    cudaFree(c->d_frames); cudaFree(c->d_sum); cudaFree(c->d_calm_total);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
@@ -458,6 +498,27 @@ int poppy_cuda_set_tile_list_capacity(poppy_cuda_ctx* c, int entries) {
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     c->list_cap = entries;
     free_chunk(c);            // reallocated with the new capacity by the next render
+    return 0;
+}
+
+int poppy_cuda_set_unsharp_mode(poppy_cuda_ctx* c, int mode) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (mode != 0 && mode != 1) return fail(c, POPPY_CUDA_ERR_INVALID, "unsharp mode must be 0 (calm analysis) or 1 (exact path everywhere)");
+    c->unsharp_mode = mode;
+    return 0;
+}
+
+int poppy_cuda_unsharp_stats(poppy_cuda_ctx* c, uint64_t* chunks_exact, uint64_t* chunks_total) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    for (auto& l : c->lane) if (l.stream) CU_TRY(c, cudaStreamSynchronize(l.stream));
+    unsigned long long v = 0;
+    CU_TRY(c, cudaMemcpy(&v, c->d_calm_total, sizeof v, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemset(c->d_calm_total, 0, sizeof v));
+    if (chunks_exact) *chunks_exact = v;
+    if (chunks_total) *chunks_total = c->calm_chunks_total;
+    c->calm_chunks_total = 0;
     return 0;
 }
 

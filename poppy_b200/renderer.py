@@ -42,6 +42,16 @@ class MorphRenderer:
         if stage_timing:
             self._check(self._lib.poppy_cuda_set_stage_timing(self._ctx, 1))
 
+    def set_unsharp_mode(self, mode: int):
+        """0: calm analysis (exact blur + median only where unsharp_mask() can change a pixel); 1: exact path everywhere."""
+        self._check(self._lib.poppy_cuda_set_unsharp_mode(self._ctx, int(mode)))
+
+    def unsharp_stats(self) -> tuple:
+        """(strip chunks that took the exact unsharp path, all strip chunks) since the last call."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.poppy_cuda_unsharp_stats(self._ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def set_tile_list_capacity(self, entries_per_frame: int):
         self._check(self._lib.poppy_cuda_set_tile_list_capacity(self._ctx, int(entries_per_frame)))
 

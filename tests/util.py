@@ -37,3 +37,14 @@ def flat_tri(tri_lists):
     offs[1:] = np.cumsum([len(t) for t in tri_lists])
     cat = np.concatenate(tri_lists).astype(np.int32) if len(tri_lists) else np.zeros((0, 3), np.int32)
     return cat, offs
+
+
+def frame_checksum(frame: np.ndarray) -> int:
+    """Position-weighted 64-bit checksum of a frame's bytes: the function of k_checksum (device) and of the
+    full-pipeline harness (oracle/ref_full_harness.cpp)."""
+    b = np.ascontiguousarray(frame).reshape(-1).astype(np.uint64)
+    i = np.arange(b.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        k = (i + np.uint64(0x9E3779B97F4A7C15)) * np.uint64(0xBF58476D1CE4E5B9)
+        k ^= k >> np.uint64(29)
+        return int(((b + np.uint64(1)) * (k | np.uint64(1))).sum(dtype=np.uint64))
