@@ -67,12 +67,15 @@ int poppy_cuda_get_info(const poppy_cuda_ctx* ctx, int* width, int* height, int*
 int poppy_cuda_set_keep_stages(poppy_cuda_ctx* ctx, int keep);       /* 1: chunk size 1, stage buffers readable */
 int poppy_cuda_set_chunk_frames(poppy_cuda_ctx* ctx, int frames);    /* frames rendered per kernel batch (>=1) */
 int poppy_cuda_set_stage_timing(poppy_cuda_ctx* ctx, int enable);    /* CUDA-event timing per kernel class */
-/* unsharp_mask stage (reference src/util.cpp:113-148, called at src/algo.cpp:263-264). mode 0 (default): the level-0
- * collapse stores the 8-bit frame itself, and the exact GaussianBlur + medianBlur + threshold path runs only on the strip
- * chunks where the range of lapBlend over a pixel's 11x11 footprint could let |x - blur| reach the 0.3 norm threshold;
- * everywhere else unsharp_mask() provably returns x. mode 1: the exact path on every pixel. Both are bit-identical. */
+/* unsharp_mask stage (reference src/util.cpp:113-148, called at src/algo.cpp:263-264): two bit-identical routes.
+ * Calm route: the level-0 collapse stores the 8-bit frame itself, and the exact GaussianBlur + medianBlur + threshold path
+ * runs only on the strip chunks where a bound on |x - blur| (second differences of the stored bytes) does not rule out the
+ * 0.3 norm threshold; everywhere else unsharp_mask() provably returns x. Dense route: the exact path on every pixel.
+ * mode 0 (default): adaptive - calm route while few chunks of recent frames needed the exact path, dense route otherwise;
+ * mode 1: dense always; mode 2: calm route always. */
 int poppy_cuda_set_unsharp_mode(poppy_cuda_ctx* ctx, int mode);
-/* Strip chunks (120 columns x 24 rows) that took the exact unsharp path / all chunks, since the last call; syncs. */
+/* Strip chunks (120 columns x 24 rows of a frame) that took the exact unsharp path / all chunks, since the last call;
+ * syncs. */
 int poppy_cuda_unsharp_stats(poppy_cuda_ctx* ctx, uint64_t* chunks_exact, uint64_t* chunks_total);
 /* Capacity (entries per frame) of the per-tile triangle lists that feed the rasteriser. The default suits any
  * Delaunay mesh; a frame whose lists do not fit is still rendered exactly (every tile then tests every triangle of
@@ -84,7 +87,16 @@ int poppy_cuda_set_tile_list_capacity(poppy_cuda_ctx* ctx, int entries_per_frame
 int poppy_cuda_set_pair(poppy_cuda_ctx* ctx, const uint8_t* bgr1, size_t step1, const uint8_t* bgr2, size_t step2,
                         const float* gabor2_bgr32f, size_t gstep);
 
-/* srcPoints1 / srcPoints2 (n x 2 float, x then y), unclipped as the caller holds them. */
+/* One image of the pair: which = 0 corrected1 (8UC3), 1 corrected2 (8UC3), 2 gabor2 (32FC3). Lets a per-frame caller
+ * re-upload only what changed between two morph_images() calls (in the reference's frame loop only corrected1 does,
+ * src/poppy.hpp:217). Asynchronous for pinned memory: poppy_cuda_sync() before the buffer is modified. */
+int poppy_cuda_set_image(poppy_cuda_ctx* ctx, int which, const void* data, size_t step);
+/* corrected1 := rendered frame `slot` of the ring, device to device: the `corrected1 = morphed.clone()` of the reference
+ * frame loop (src/poppy.hpp:217) for callers that drive the recurrence one render call per frame. */
+int poppy_cuda_set_source1_from_slot(poppy_cuda_ctx* ctx, int slot);
+
+/* srcPoints1 / srcPoints2 (n x 2 float, x then y), unclipped as the caller holds them. n < 3 is allowed (no triangles:
+ * the frame is the blend of the unwarped pair, as in the reference). */
 int poppy_cuda_set_points(poppy_cuda_ctx* ctx, const float* pts1_xy, const float* pts2_xy, int n);
 
 /* Render n_frames frames into the HBM frame ring (slots 0 .. n_frames-1).

@@ -52,6 +52,8 @@ def load():
         "poppy_cuda_unsharp_stats": (i32, [vp, u64p, u64p]),
         "poppy_cuda_set_tile_list_capacity": (i32, [vp, i32]),
         "poppy_cuda_set_pair": (i32, [vp, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t]),
+        "poppy_cuda_set_image": (i32, [vp, i32, vp, C.c_size_t]),
+        "poppy_cuda_set_source1_from_slot": (i32, [vp, i32]),
         "poppy_cuda_set_points": (i32, [vp, vp, vp, i32]),
         "poppy_cuda_render": (i32, [vp, i32, vp, vp, vp, vp, i32]),
         "poppy_cuda_render_range": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
@@ -85,7 +87,7 @@ CUDA_ABI_SYMBOLS = [
     "poppy_cuda_checksum", "poppy_cuda_sync", "poppy_cuda_get_stream", "poppy_cuda_last_render_ms",
     "poppy_cuda_launch_count", "poppy_cuda_stage_times", "poppy_cuda_debug_read", "poppy_cuda_last_error",
     "poppy_cuda_version", "poppy_cuda_get_info", "poppy_cuda_set_tile_list_capacity", "poppy_cuda_set_unsharp_mode",
-    "poppy_cuda_unsharp_stats",
+    "poppy_cuda_unsharp_stats", "poppy_cuda_set_image", "poppy_cuda_set_source1_from_slot",
 ]
 HOST_ABI_SYMBOLS = [
     "poppy_host_morph_points", "poppy_host_triangulate", "poppy_host_chain_ratio", "poppy_host_plan_create",

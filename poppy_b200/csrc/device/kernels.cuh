@@ -21,6 +21,13 @@ inline void ensure_smem_attr(K kernel, size_t bytes, SmemAttrOnce& once) {
     }
 }
 
+// A CUtensorMap (cuda.h), kept opaque here: built on the host by cuTensorMapEncodeTiled (poppy_cuda.cu), passed to the
+// kernels as a __grid_constant__ parameter and named by cp.async.bulk.tensor.
+struct alignas(64) TmaMap { unsigned long long v[16]; };
+// The four box sources of one level's collapse (k_collapse_tma): fine level (warped word planes at level 0, the Gaussian
+// planes otherwise), level-0 mask (level 0 only), coarse Gaussian planes, coarse out planes.
+struct CollapseMaps { TmaMap fine, mask, gc, oc; };
+
 // ---- kernels_geometry.cu -----------------------------------------------------------------------------------------
 void launch_clip_points(cudaStream_t st, const float2* in, float2* out, int n, int cols, int rows);
 void launch_lerp_points(cudaStream_t st, const float2* p1, size_t p1_frame_stride, const float2* p2,
@@ -62,20 +69,21 @@ void launch_pyr_down(cudaStream_t st, const float* src, LevelDesc sl, float* dst
 // resultSmallest = left*mask + right*(1-mask) at the coarsest level (blend.hpp:68-69)
 void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* out, int frames);
 // out[k] = pyrUp(out[k+1]) + (G_l[k]-pyrUp(G_l[k+1]))*m[k] + (G_r[k]-pyrUp(G_r[k+1]))*(1-m[k])   (blend.hpp:45-77)
+// maps (nullable): tensor maps of the level's planes; with them interior tiles are fed by a TMA producer warp
 void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
-                     LevelDesc cl, float* out_fine, int frames);
+                     LevelDesc cl, float* out_fine, int frames, const CollapseMaps* maps);
 // same for level 0, whose Gaussian level is the warped 8-bit pair + the level-0 mask planes
 // tile_flags (nullable): per frame and 128x32 tile, 0 = the tile is not needed (calm, see below)
 void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
                       size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
-                      float* out_fine, LevelDesc ol, int frames, const unsigned char* tile_flags);
+                      float* out_fine, LevelDesc ol, int frames, const unsigned char* tile_flags, const CollapseMaps* maps);
 // level-0 collapse fused with convertTo(CV_8U, 255): stores cvRound(255 out[0]) into the frame ring (exactly the frame
 // wherever unsharp_mask() leaves the pixel untouched) and, per 4x8-pixel block and channel, whether out[0] left [0, 1] by
 // more than 0.001 there: ex[(f*3 + c) * ex_stride + by * ex_pitch + bx]
 void launch_collapse0_emit(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
                            size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
                            const FrameParams* fp, uint8_t* frames_base, size_t frame_bytes, unsigned char* ex, int ex_pitch,
-                           size_t ex_stride, int frames);
+                           size_t ex_stride, int frames, const CollapseMaps* maps);
 
 // ---- kernels_unsharp.cu ------------------------------------------------------------------------------------------
 // unsharp_mask(lapBlend, 1, amount, 0.3) + convertTo(CV_8U, 255)   (reference src/algo.cpp:263-265, util.cpp:113-148)

@@ -637,17 +637,29 @@ __device__ __forceinline__ void up_row(const float* __restrict__ row, int cw, in
     for (int i = 0; i < 4; ++i) o[i] = __fmul_rn(o[i], 1.f / 64);
 }
 
-// vertical pass of cv::pyrUp (pyramids.cpp:929-993) on pre-scaled row-pass values:
-// even fine row (r0 + 6 r1) + r2, odd fine row (r1 + r2) * 4
-__device__ __forceinline__ float up_even(float h0, float h1, float h2) {
-    return __fadd_rn(__fadd_rn(h0, __fmul_rn(h1, 6.f)), h2);
-}
-__device__ __forceinline__ float up_odd(float h1, float h2) { return __fmul_rn(__fadd_rn(h1, h2), 4.f); }
+// vertical pass of cv::pyrUp (pyramids.cpp:929-993) on pre-scaled row-pass values: even fine row (r0 + 6 r1) + r2, odd fine
+// row (r1 + r2) * 4; then out = up_o + ((gl - up_l) * m + (gr - up_r) * (1 - m))   (blend.hpp:52-53,70-72,62-63) - both in the
+// column-pair forms below.
 
-// out = up_o + ((gl - up_l) * m + (gr - up_r) * (1 - m))        (blend.hpp:52-53,70-72,62-63)
-__device__ __forceinline__ float blend1(float gl, float gr, float m, float ul, float ur, float uo) {
-    const float lap_l = __fsub_rn(gl, ul), lap_r = __fsub_rn(gr, ur);
-    return __fadd_rn(uo, __fadd_rn(__fmul_rn(lap_l, m), __fmul_rn(lap_r, __fsub_rn(1.f, m))));
+// ---- packed fp32 (sm_100 FADD2 / FMUL2 / FFMA2: two individually rounded IEEE operations per issue slot) ------------------
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (seen with CUDA 12.9), which would
+// change the rounding. A product that feeds an addition is therefore issued as fma(a, b, -0.0) with the -0.0 read from
+// constant memory (opaque to the compiler): a * b + (-0.0) rounds once to exactly round(a * b), signed zeros included,
+// and an FFMA2 cannot be merged with the addition that follows. Multiplications by powers of two are exact, so their
+// contraction is harmless and they use FMUL2. a - b is fma(b, -1, a): one rounding of the exact difference.
+__constant__ float2 c_negzero2 = {-0.0f, -0.0f};
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 psub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+__device__ __forceinline__ float2 pmul_rounded(float2 a, float2 b, float2 nz) { return __ffma2_rn(a, b, nz); }
+__device__ __forceinline__ float2 pscale(float2 a, float pow2) { return __fmul2_rn(a, make_float2(pow2, pow2)); }
+// column-pair forms of up_even / up_odd / blend1
+__device__ __forceinline__ float2 up_even2(float2 h0, float2 h1, float2 h2, float2 nz) {
+    return padd(padd(h0, pmul_rounded(h1, make_float2(6.f, 6.f), nz)), h2);
+}
+__device__ __forceinline__ float2 up_odd2(float2 h1, float2 h2) { return pscale(padd(h1, h2), 4.f); }
+__device__ __forceinline__ float2 blend2(float2 gl, float2 gr, float2 m, float2 ul, float2 ur, float2 uo, float2 nz) {
+    const float2 lap_l = psub(gl, ul), lap_r = psub(gr, ur), anti = psub(make_float2(1.f, 1.f), m);
+    return padd(uo, padd(pmul_rounded(lap_l, m, nz), pmul_rounded(lap_r, anti, nz)));
 }
 
 // ---- cp.async (LDGSTS) staging of the collapse kernel's loads -----------------------------------------------------------
@@ -797,6 +809,7 @@ __device__ __forceinline__ void emit_flush(EmitCtx& E, int fy, int fx) {
 }
 // INTERIOR tiles (all 96 threads of the CTA in step, w % 4 == 0): the three channel warps interleave their bytes in
 // shared memory and every warp stores one contiguous 128-byte third of each 384-byte frame row segment
+template <bool NAMED_BAR = false>
 __device__ __forceinline__ void emit_rows_interior(EmitCtx& E, int k, const float (&e)[4], const float (&o)[4], int c, int lane,
                                                    int w, int fy, int fx0) {
     unsigned char* b = E.rowbuf + (k & 1) * 768;
@@ -805,7 +818,10 @@ __device__ __forceinline__ void emit_rows_interior(EmitCtx& E, int k, const floa
         b[12 * lane + 3 * i + c] = (unsigned char)(__float_as_uint(emit_u8(E, e[i])) & 255u);
         b[384 + 12 * lane + 3 * i + c] = (unsigned char)(__float_as_uint(emit_u8(E, o[i])) & 255u);
     }
-    __syncthreads();            // one barrier per step: the buffers alternate with the step parity
+    // one barrier per step: the buffers alternate with the step parity (NAMED_BAR: the three channel warps of the TMA kernel,
+    // whose producer warp does not take part)
+    if (NAMED_BAR) asm volatile("bar.sync 1, 96;\n" ::: "memory");
+    else __syncthreads();
     const uint32_t* bw = reinterpret_cast<const uint32_t*>(b);
     const uint32_t w0 = bw[32 * c + lane], w1 = bw[96 + 32 * c + lane];
     uint32_t* drow = reinterpret_cast<uint32_t*>(E.frame + ((size_t)fy * w + fx0) * 3) + 32 * c + lane;
@@ -834,6 +850,7 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
     const float* __restrict__ pl = A.gc + (size_t)c * A.cstride;
     const float* __restrict__ pr = A.gc + (size_t)(3 + c) * A.cstride;
     const float* __restrict__ po = A.oc + (size_t)c * A.cstride;
+    const float2 nz = c_negzero2;
     float hm[3][4], h0[3][4], hp[3][4];          // row-pass values of coarse rows sy-1, sy, sy+1 for (left, right, out)
     auto coarse_now = [&](int cy, float (&h)[3][4]) {            // load where consumed
         const size_t off = (size_t)cy * A.cpitch;
@@ -977,12 +994,23 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
         }
         float e[4], o[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            e[i] = blend1(gl[0][i], gr[0][i], mk[0][i], up_even(hm[0][i], h0[0][i], hp[0][i]), up_even(hm[1][i], h0[1][i], hp[1][i]),
-                          up_even(hm[2][i], h0[2][i], hp[2][i]));
-            if (two)
-                o[i] = blend1(gl[1][i], gr[1][i], mk[1][i], up_odd(h0[0][i], hp[0][i]), up_odd(h0[1][i], hp[1][i]),
-                              up_odd(h0[2][i], hp[2][i]));
+        for (int i = 0; i < 4; i += 2) {              // two adjacent columns per packed operation
+            float2 u[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                u[p] = up_even2(make_float2(hm[p][i], hm[p][i + 1]), make_float2(h0[p][i], h0[p][i + 1]),
+                                make_float2(hp[p][i], hp[p][i + 1]), nz);
+            const float2 ev = blend2(make_float2(gl[0][i], gl[0][i + 1]), make_float2(gr[0][i], gr[0][i + 1]),
+                                     make_float2(mk[0][i], mk[0][i + 1]), u[0], u[1], u[2], nz);
+            e[i] = ev.x; e[i + 1] = ev.y;
+            if (two) {
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+                    u[p] = up_odd2(make_float2(h0[p][i], h0[p][i + 1]), make_float2(hp[p][i], hp[p][i + 1]));
+                const float2 ov = blend2(make_float2(gl[1][i], gl[1][i + 1]), make_float2(gr[1][i], gr[1][i + 1]),
+                                         make_float2(mk[1][i], mk[1][i + 1]), u[0], u[1], u[2], nz);
+                o[i] = ov.x; o[i + 1] = ov.y;
+            }
         }
         if (EMIT) {
             if (INTERIOR && emit_words) emit_rows_interior(*E, k, e, o, c, lane, A.w, fy, fx0);
@@ -1057,6 +1085,195 @@ k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride,
     }
 }
 
+// ---- collapse with a TMA producer warp --------------------------------------------------------------------------------
+// Interior tiles of k_collapse_tma: a fourth warp keeps a ring of CT_NS stages full with tensor-map TMA box copies
+// (cp.async.bulk.tensor.3d, SASS UTMALDG): per step one box for the two fine rows of the warped pair (both images, 2 KB),
+// one for the mask rows, one for the coarse row of the six Gaussian planes and one for the coarse row of the three out
+// planes - four instructions per step and CTA instead of the 27 row-segment copies of the per-warp rings above, and the
+// three channel warps share the fine data instead of staging it three times. Full/empty mbarriers connect the producer to
+// the channel warps; border tiles run the generic body.
+constexpr int CT_NS = 3;
+template <bool L0> struct CtStage;
+template <> struct __align__(128) CtStage<true> {
+    uint32_t fine[2][2][128];            // [image][row][column]: box {128, 2, 2} of the warped word planes
+    float mask[2][128];                  // box {128, 2, 1} of the level-0 mask
+    __align__(128) float gc[6][72];      // box {72, 1, 6}: coarse columns a0-4 .. a0+67 of left B,G,R, right B,G,R
+    __align__(128) float oc[3][72];      // box {72, 1, 3} of the coarse out planes
+};
+template <> struct __align__(128) CtStage<false> {
+    float fine[7][2][128];               // box {128, 2, 7} of the fine Gaussian planes
+    __align__(128) float gc[6][72];
+    __align__(128) float oc[3][72];
+};
+struct CtBars { unsigned long long full[CT_NS], empty[CT_NS]; };
+template <bool L0> __host__ __device__ constexpr unsigned ct_stage_bytes() { return (L0 ? 2 * 2 * 128 * 4 + 2 * 128 * 4 : 7 * 2 * 128 * 4) + 6 * 72 * 4 + 3 * 72 * 4; }
+template <bool L0, bool EMIT> constexpr size_t ct_smem() { return CT_NS * sizeof(CtStage<L0>) + 128 + (EMIT ? 2 * 2 * 384 : 0); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const TmaMap* map, int x, int y, int z, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// channel warp c of an interior tile
+template <bool L0, bool EMIT>
+__device__ __forceinline__ void collapse_consume(const CollapseArgs& A, int c, int fx, int cy0, int lane, const CtStage<L0>* stages,
+                                                 CtBars* bars, EmitCtx* E, bool emit_words) {
+    const float2 nz = c_negzero2;
+    const float* __restrict__ pl = A.gc + (size_t)c * A.cstride;
+    const float* __restrict__ pr = A.gc + (size_t)(3 + c) * A.cstride;
+    const float* __restrict__ po = A.oc + (size_t)c * A.cstride;
+    const int fx0 = fx - 4 * lane;
+    float hm[3][4], h0[3][4], hp[3][4];
+    {   // coarse rows cy0 - 1 and cy0: loaded directly, once per tile
+        const size_t o1 = (size_t)(cy0 - 1) * A.cpitch, o2 = (size_t)cy0 * A.cpitch;
+        up_row<true>(pl + o1, A.cw, A.w, fx, hm[0]); up_row<true>(pr + o1, A.cw, A.w, fx, hm[1]); up_row<true>(po + o1, A.cw, A.w, fx, hm[2]);
+        up_row<true>(pl + o2, A.cw, A.w, fx, h0[0]); up_row<true>(pr + o2, A.cw, A.w, fx, h0[1]); up_row<true>(po + o2, A.cw, A.w, fx, h0[2]);
+    }
+    float* __restrict__ orow = EMIT ? nullptr : A.out + (size_t)c * A.ostride + (size_t)(2 * cy0) * A.opitch + fx;
+#pragma unroll 1
+    for (int k = 0; k < CL_R; ++k) {
+        const int s = k % CT_NS, fy = 2 * (cy0 + k);
+        mbar_wait(&bars->full[s], (unsigned)(k / CT_NS) & 1u);
+        const CtStage<L0>& S = stages[s];
+        float gl[2][4], gr[2][4], mk[2][4];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const float* seg = (p == 0 ? S.gc[c] : p == 1 ? S.gc[3 + c] : S.oc[c]) + 4 + 2 * lane;      // coarse column a0 + 2 * lane
+            UpRaw u;
+            u.cm = seg[-1]; u.c01 = *reinterpret_cast<const float2*>(seg); u.cp = seg[2];
+            up_row_raw(u, hp[p]);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            FineRaw<L0> rf;
+            if (L0) {
+                const CtStage<true>& T = reinterpret_cast<const CtStage<true>&>(S);
+                fine_from_rows(reinterpret_cast<const float4*>(T.fine[0][r])[lane], reinterpret_cast<const float4*>(T.fine[1][r])[lane],
+                               reinterpret_cast<const float4*>(T.mask[r])[lane], rf);
+            } else {
+                const CtStage<false>& T = reinterpret_cast<const CtStage<false>&>(S);
+                fine_from_rows(reinterpret_cast<const float4*>(T.fine[c][r])[lane], reinterpret_cast<const float4*>(T.fine[3 + c][r])[lane],
+                               reinterpret_cast<const float4*>(T.fine[6][r])[lane], rf);
+            }
+            fine_unpack(rf, c, gl[r], gr[r], mk[r]);
+        }
+        // the stage is in registers: release it to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->empty[s]);
+        float e[4], o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i += 2) {
+            float2 u[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                u[p] = up_even2(make_float2(hm[p][i], hm[p][i + 1]), make_float2(h0[p][i], h0[p][i + 1]),
+                                make_float2(hp[p][i], hp[p][i + 1]), nz);
+            const float2 ev = blend2(make_float2(gl[0][i], gl[0][i + 1]), make_float2(gr[0][i], gr[0][i + 1]),
+                                     make_float2(mk[0][i], mk[0][i + 1]), u[0], u[1], u[2], nz);
+            e[i] = ev.x; e[i + 1] = ev.y;
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                u[p] = up_odd2(make_float2(h0[p][i], h0[p][i + 1]), make_float2(hp[p][i], hp[p][i + 1]));
+            const float2 ov = blend2(make_float2(gl[1][i], gl[1][i + 1]), make_float2(gr[1][i], gr[1][i + 1]),
+                                     make_float2(mk[1][i], mk[1][i + 1]), u[0], u[1], u[2], nz);
+            o[i] = ov.x; o[i + 1] = ov.y;
+        }
+        if (EMIT) {
+            if (emit_words) emit_rows_interior<true>(*E, k, e, o, c, lane, A.w, fy, fx0);
+            else emit_rows_generic(*E, k, e, o, true, c, A.w, fy, fx);
+        } else {
+            *reinterpret_cast<float4*>(orow) = make_float4(e[0], e[1], e[2], e[3]);
+            *reinterpret_cast<float4*>(orow + A.opitch) = make_float4(o[0], o[1], o[2], o[3]);
+            orow += 2 * (size_t)A.opitch;
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { hm[p][i] = h0[p][i]; h0[p][i] = hp[p][i]; }
+    }
+}
+
+// block (32, 4): warps 0-2 = colour channels, warp 3 = TMA producer; grid (ceil(w/128), ceil(h/32), frames).
+// tm_fine: L0 -> the warped word planes [2 * frames][h][wpitch], else the fine Gaussian planes [7 * frames][h][fpitch];
+// tm_mask (L0): the level-0 mask planes [frames][h][mpitch]; tm_gc / tm_oc: the coarse Gaussian / out planes.
+template <bool L0, bool EMIT>
+__global__ void __launch_bounds__(128, L0 ? 6 : 5)
+k_collapse_tma(const __grid_constant__ TmaMap tm_fine, const __grid_constant__ TmaMap tm_mask, const __grid_constant__ TmaMap tm_gc,
+               const __grid_constant__ TmaMap tm_oc, const uint32_t* __restrict__ warped, int wpitch, size_t wstride,
+               const float* __restrict__ mask0, int mpitch, size_t m0stride, const float* __restrict__ g_fine, int w, int h, int fpitch,
+               size_t fstride, const float* __restrict__ g_coarse, const float* __restrict__ out_coarse, int cw, int ch, int cpitch,
+               size_t cstride, float* __restrict__ out_fine, int opitch, size_t ostride, const unsigned char* __restrict__ tile_flags,
+               const FrameParams* __restrict__ fp, uint8_t* __restrict__ frames_base, size_t frame_bytes, unsigned char* __restrict__ ex,
+               int ex_pitch, size_t ex_stride) {
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    const int f = blockIdx.z, warp = threadIdx.y, lane = threadIdx.x, c = warp < 3 ? warp : 0;
+    if (tile_flags && !tile_flags[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
+    const int fx = blockIdx.x * 128 + 4 * lane, cy0 = blockIdx.y * CL_R;
+    CollapseArgs A;
+    A.w1 = L0 ? warped + (size_t)f * 2 * wstride : nullptr; A.w2 = L0 ? A.w1 + wstride : nullptr; A.wpitch = wpitch;
+    A.mask0 = L0 ? mask0 + (size_t)f * m0stride : nullptr; A.mpitch = mpitch;
+    A.gfine = L0 ? nullptr : g_fine + (size_t)f * 7 * fstride; A.fpitch = fpitch; A.fstride = fstride;
+    A.gc = g_coarse + (size_t)f * 7 * cstride; A.oc = out_coarse + (size_t)f * 3 * cstride;
+    A.cw = cw; A.ch = ch; A.cpitch = cpitch; A.cstride = cstride;
+    A.out = EMIT ? nullptr : out_fine + (size_t)f * 3 * ostride; A.opitch = opitch; A.ostride = ostride; A.w = w; A.h = h;
+    CtStage<L0>* stages = reinterpret_cast<CtStage<L0>*>(smem_dyn);
+    CtBars* bars = reinterpret_cast<CtBars*>(smem_dyn + CT_NS * sizeof(CtStage<L0>));
+    EmitCtx E;
+    bool emit_words = false;
+    if (EMIT) {
+        E.frame = frames_base + (size_t)fp[f].dst_slot * frame_bytes;
+        E.ex = ex + ((size_t)f * 3 + c) * ex_stride; E.ex_pitch = ex_pitch;
+        E.rowbuf = smem_dyn + CT_NS * sizeof(CtStage<L0>) + 128;
+        E.excess = 0.f;
+        emit_words = (w & 3) == 0 && (reinterpret_cast<size_t>(E.frame) & 3) == 0;
+    }
+    const int a = fx >> 1;
+    const bool lane_in = a >= 1 && a + 2 <= cw - 1;                       // implies fx + 3 < w
+    const bool rows_in = cy0 >= 1 && cy0 + CL_R <= ch - 1 && 2 * (cy0 + CL_R) <= h;
+    if (__all_sync(FULL, lane_in && rows_in)) {                           // the same decision in all four warps
+        if (warp == 3 && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < CT_NS; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 3); }
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+        if (warp == 3) {
+            if (lane == 0) {
+                const int fx0 = blockIdx.x * 128, a0 = fx0 >> 1;
+#pragma unroll 1
+                for (int k = 0; k < CL_R; ++k) {
+                    const int s = k % CT_NS;
+                    if (k >= CT_NS) mbar_wait(&bars->empty[s], (unsigned)(k / CT_NS - 1) & 1u);
+                    // the channel warps read the stage through the generic proxy; order those reads before the TMA writes
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                    unsigned long long* bar = &bars->full[s];
+                    mbar_expect_tx(bar, ct_stage_bytes<L0>());
+                    CtStage<L0>& S = stages[s];
+                    if (L0) {
+                        CtStage<true>& T = reinterpret_cast<CtStage<true>&>(S);
+                        tma_load_3d(T.fine, &tm_fine, fx0, 2 * (cy0 + k), 2 * f, bar);
+                        tma_load_3d(T.mask, &tm_mask, fx0, 2 * (cy0 + k), f, bar);
+                    } else {
+                        CtStage<false>& T = reinterpret_cast<CtStage<false>&>(S);
+                        tma_load_3d(T.fine, &tm_fine, fx0, 2 * (cy0 + k), 7 * f, bar);
+                    }
+                    tma_load_3d(S.gc, &tm_gc, a0 - 4, cy0 + k + 1, 7 * f, bar);
+                    tma_load_3d(S.oc, &tm_oc, a0 - 4, cy0 + k + 1, 3 * f, bar);
+                }
+            }
+            return;
+        }
+        collapse_consume<L0, EMIT>(A, c, fx, cy0, lane, stages, bars, &E, emit_words);
+    } else if (warp < 3 && fx < w) {
+        collapse_body<L0, false, false, EMIT>(A, c, fx, cy0, nullptr, lane, nullptr, &E, false);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // A/B switch for profiling: POPPY_CUDA_NO_BULK=1 selects the register-prefetch bodies everywhere
 static bool use_bulk() {
@@ -1096,21 +1313,46 @@ void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* 
 
 constexpr size_t CL_EMIT_SMEM = CL_SMEM + 2 * 2 * 384;
 
+// A/B switch: POPPY_CUDA_TMA=0 keeps the per-warp staging rings (k_collapse_roll) on interior tiles
+static bool use_tma() {
+    static const bool v = [] { const char* e = std::getenv("POPPY_CUDA_TMA"); return !(e && e[0] == '0'); }();
+    return v && use_bulk();
+}
+
 void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
-                     LevelDesc cl, float* out_fine, int frames) {
+                     LevelDesc cl, float* out_fine, int frames, const CollapseMaps* maps) {
+    const dim3 grid(div_up(fl.w, 128), div_up(fl.h, 2 * CL_R), frames);
+    if (maps && use_tma()) {
+        static SmemAttrOnce done;
+        ensure_smem_attr(k_collapse_tma<false, false>, ct_smem<false, false>(), done);
+        k_collapse_tma<false, false><<<grid, dim3(32, 4), ct_smem<false, false>(), st>>>(
+            maps->fine, maps->mask, maps->gc, maps->oc, nullptr, 0, 0, nullptr, 0, 0, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse,
+            out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, out_fine, fl.pitch, fl.plane_stride, nullptr, nullptr, nullptr, 0, nullptr, 0, 0);
+        return;
+    }
     static SmemAttrOnce done;
     ensure_smem_attr(k_collapse_roll<false, false>, CL_SMEM, done);
-    k_collapse_roll<false, false><<<dim3(div_up(fl.w, 128), div_up(fl.h, 2 * CL_R), frames), dim3(32, 3), CL_SMEM, st>>>(
+    k_collapse_roll<false, false><<<grid, dim3(32, 3), CL_SMEM, st>>>(
         nullptr, 0, 0, nullptr, 0, 0, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
         cl.plane_stride, out_fine, fl.pitch, fl.plane_stride, collapse_bulk_mode() & 2 ? 1 : 0, nullptr, nullptr, nullptr, 0, nullptr, 0, 0);
 }
 
 void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
                       size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
-                      float* out_fine, LevelDesc ol, int frames, const unsigned char* tile_flags) {
+                      float* out_fine, LevelDesc ol, int frames, const unsigned char* tile_flags, const CollapseMaps* maps) {
+    const dim3 grid(div_up(w, 128), div_up(h, 2 * CL_R), frames);
+    if (maps && use_tma()) {
+        static SmemAttrOnce done;
+        ensure_smem_attr(k_collapse_tma<true, false>, ct_smem<true, false>(), done);
+        k_collapse_tma<true, false><<<grid, dim3(32, 4), ct_smem<true, false>(), st>>>(
+            maps->fine, maps->mask, maps->gc, maps->oc, warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse,
+            out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, out_fine, ol.pitch, ol.plane_stride, tile_flags, nullptr, nullptr, 0, nullptr,
+            0, 0);
+        return;
+    }
     static SmemAttrOnce done;
     ensure_smem_attr(k_collapse_roll<true, false>, CL_SMEM, done);
-    k_collapse_roll<true, false><<<dim3(div_up(w, 128), div_up(h, 2 * CL_R), frames), dim3(32, 3), CL_SMEM, st>>>(
+    k_collapse_roll<true, false><<<grid, dim3(32, 3), CL_SMEM, st>>>(
         warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
         cl.plane_stride, out_fine, ol.pitch, ol.plane_stride, collapse_bulk_mode() & 1 ? 1 : 0, tile_flags, nullptr, nullptr, 0, nullptr,
         0, 0);
@@ -1119,10 +1361,19 @@ void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_
 void launch_collapse0_emit(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
                            size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
                            const FrameParams* fp, uint8_t* frames_base, size_t frame_bytes, unsigned char* ex, int ex_pitch,
-                           size_t ex_stride, int frames) {
+                           size_t ex_stride, int frames, const CollapseMaps* maps) {
+    const dim3 grid(div_up(w, 128), div_up(h, 2 * CL_R), frames);
+    if (maps && use_tma()) {
+        static SmemAttrOnce done;
+        ensure_smem_attr(k_collapse_tma<true, true>, ct_smem<true, true>(), done);
+        k_collapse_tma<true, true><<<grid, dim3(32, 4), ct_smem<true, true>(), st>>>(
+            maps->fine, maps->mask, maps->gc, maps->oc, warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse,
+            out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, nullptr, 0, 0, nullptr, fp, frames_base, frame_bytes, ex, ex_pitch, ex_stride);
+        return;
+    }
     static SmemAttrOnce done;
     ensure_smem_attr(k_collapse_roll<true, true>, CL_EMIT_SMEM, done);
-    k_collapse_roll<true, true><<<dim3(div_up(w, 128), div_up(h, 2 * CL_R), frames), dim3(32, 3), CL_EMIT_SMEM, st>>>(
+    k_collapse_roll<true, true><<<grid, dim3(32, 3), CL_EMIT_SMEM, st>>>(
         warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
         cl.plane_stride, nullptr, 0, 0, collapse_bulk_mode() & 1 ? 1 : 0, nullptr, fp, frames_base, frame_bytes, ex, ex_pitch,
         ex_stride);

@@ -90,7 +90,7 @@ int poppy_host_plan_create(poppy_host_plan** out, const float* p1, const float* 
                            const float* shape_ratio, int chain, int threads) {
     if (!out) return host_fail(POPPY_CUDA_ERR_INVALID, "out is null");
     *out = nullptr;
-    if (!p1 || !p2 || !shape_ratio || n < 3 || n_frames < 1) return host_fail(POPPY_CUDA_ERR_INVALID, "bad argument");
+    if (!p1 || !p2 || !shape_ratio || n < 0 || n_frames < 1) return host_fail(POPPY_CUDA_ERR_INVALID, "bad argument");
     poppy_host_plan* plan = new poppy_host_plan();
     plan->n = n;
     plan->frames = n_frames;
@@ -177,7 +177,7 @@ void poppy_host_plan_destroy(poppy_host_plan* plan) { delete plan; }
 int poppy_morph_images(poppy_cuda_ctx* ctx, const uint8_t* c1, size_t step1, const uint8_t* c2, size_t step2,
                        const float* gabor2, size_t gstep, const float* sp1, const float* sp2, int n,
                        double shape_ratio, double mask_ratio, uint8_t* dst, size_t dst_step, float* morphed_xy) {
-    if (!ctx || !c1 || !c2 || !gabor2 || !sp1 || !sp2 || !dst) return host_fail(POPPY_CUDA_ERR_INVALID, "null argument");
+    if (!ctx || !c1 || !c2 || !gabor2 || !dst || n < 0 || (n > 0 && (!sp1 || !sp2))) return host_fail(POPPY_CUDA_ERR_INVALID, "null argument");
     int w = 0, h = 0, max_tri = 0;
     if (int rc = poppy_cuda_get_info(ctx, &w, &h, nullptr, nullptr, &max_tri, nullptr)) return host_fail(rc, "bad context");
     // host stages, reference src/algo.cpp:184-213

@@ -69,7 +69,11 @@ double morph_images(const Image8& img1, const Image8& /*img2*/, const Image8& co
     clip_points(srcPoints1, w, h);
     clip_points(srcPoints2, w, h);
     morphedPoints.resize(n);
-    poppy_host_morph_points(&srcPoints1[0].x, &srcPoints2[0].x, n, shapeRatio, w, h, &morphedPoints[0].x);
+    static const float none[2] = {0.f, 0.f};
+    const float* p1 = n ? &srcPoints1.data()->x : none;
+    const float* p2 = n ? &srcPoints2.data()->x : none;
+    float* mp = n ? &morphedPoints.data()->x : nullptr;
+    if (n) poppy_host_morph_points(p1, p2, n, shapeRatio, w, h, mp);
     std::vector<int32_t> tri;
     std::string err;
     if (!triangulate_points(morphedPoints, w, h, tri, &err)) throw MorphError("morph_images: " + err);
@@ -78,14 +82,14 @@ double morph_images(const Image8& img1, const Image8& /*img2*/, const Image8& co
     std::lock_guard<std::mutex> lock(g_mu);
     poppy_cuda_ctx* c = context_for(w, h, (int)Settings::instance().pyramid_levels, n, n_tri, 1);
     cu(c, poppy_cuda_set_pair(c, corrected1.data, corrected1.step, corrected2.data, corrected2.step, gabor2.data, gabor2.step));
-    cu(c, poppy_cuda_set_points(c, &srcPoints1[0].x, &srcPoints2[0].x, n));
+    cu(c, poppy_cuda_set_points(c, p1, p2, n));
     const float s = (float)shapeRatio;
     const int32_t offs[2] = {0, n_tri};
     cu(c, poppy_cuda_render(c, 1, &s, &maskRatio, tri.data(), offs, 0));
     if (dst.cols != w || dst.rows != h || dst.data == nullptr) dst.create(w, h);
     cu(c, poppy_cuda_download(c, 0, 1, dst.data, dst.step, dst.step * h));
     // the device recomputes morph_points(); hand back its copy (bit-identical to the host's, see tests)
-    cu(c, poppy_cuda_get_morphed_points(c, 0, &morphedPoints[0].x));
+    if (n) cu(c, poppy_cuda_get_morphed_points(c, 0, mp));
     cu(c, poppy_cuda_sync(c));
     return 0;
 }
@@ -100,7 +104,10 @@ void morph_sequence(const Image8& corrected1, const Image8& corrected2, const Im
     std::vector<double> mask(N);
     for (int j = 0; j < N; ++j) { mask[j] = poppy_host_chain_ratio(j, N); ratio[j] = (float)mask[j]; }
     poppy_host_plan* plan = nullptr;
-    if (poppy_host_plan_create(&plan, &srcPoints1[0].x, &srcPoints2[0].x, n, w, h, N, ratio.data(), 1, 0) != 0)
+    static const float none[2] = {0.f, 0.f};
+    const float* p1 = n ? &srcPoints1.data()->x : none;
+    const float* p2 = n ? &srcPoints2.data()->x : none;
+    if (poppy_host_plan_create(&plan, p1, p2, n, w, h, N, ratio.data(), 1, 0) != 0)
         throw MorphError(std::string("morph_sequence: ") + poppy_host_last_error());
     struct PlanGuard { poppy_host_plan* p; ~PlanGuard() { poppy_host_plan_destroy(p); } } guard{plan};
     const int32_t *tri = nullptr, *offs = nullptr;
@@ -110,7 +117,7 @@ void morph_sequence(const Image8& corrected1, const Image8& corrected2, const Im
     std::lock_guard<std::mutex> lock(g_mu);
     poppy_cuda_ctx* c = context_for(w, h, (int)Settings::instance().pyramid_levels, n, max_tri, N);
     cu(c, poppy_cuda_set_pair(c, corrected1.data, corrected1.step, corrected2.data, corrected2.step, gabor2.data, gabor2.step));
-    cu(c, poppy_cuda_set_points(c, &srcPoints1[0].x, &srcPoints2[0].x, n));
+    cu(c, poppy_cuda_set_points(c, p1, p2, n));
     cu(c, poppy_cuda_render(c, N, ratio.data(), mask.data(), tri, offs, 1));
     Image8 frame;
     frame.create(w, h);

@@ -8,6 +8,7 @@
 //   chunk scratch (xB): FrameParams; triangle indices; TriInverse / TriRaster records; triangle-ID map int32 [H][W];
 //                       warped pair 2 x uint32 BGRX [H][pitch0]; Gaussian levels 1..L (7 planes); collapsed levels 0..L
 //                       (3 planes); level-0 blend mask float [H][pitch0]
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -46,6 +47,9 @@ struct poppy_cuda_ctx {
     int want_chunk = 0;
     bool keep_stages = false, stage_timing = false, single_lane = false;
     bool have_pair = false, have_points = false;
+    bool have_image[3] = {false, false, false};
+    uint8_t* d_stage_u8 = nullptr;       // upload staging of set_image, kept between calls
+    float* d_stage_f32 = nullptr;
     int n_points = 0, last_frames = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -89,19 +93,28 @@ struct poppy_cuda_ctx {
         unsigned char* d_excess = nullptr;
         unsigned char *d_block_dev = nullptr, *d_block_flags = nullptr, *d_chunk_flags = nullptr, *d_tile_flags = nullptr;
         int* d_calm_counts = nullptr;
+        int* h_calm_counts = nullptr;        // pinned: flagged strip chunks per frame of the lane's last calm-route chunk
+        cudaEvent_t ev_calm = nullptr;
+        int calm_pending = 0;                // frames whose counts are on their way to h_calm_counts
+        std::vector<CollapseMaps> maps;      // tensor maps of level k's collapse (index k); empty = no TMA path
         FrameParams* h_fp = nullptr;         // pinned staging
         int32_t* h_tri = nullptr;
     } lane[4];
     int want_lanes = 3;                      // POPPY_CUDA_LANES (1..4)
     int n_lanes = 0;                         // lanes allocated (0 = none yet)
     int n_tiles = 0, list_cap = 0;
-    // unsharp stage: 0 = the fused level-0 collapse stores the frame and only strip chunks that can reach the unsharp
-    // threshold run the exact blur + median path; 1 = the exact path everywhere (A/B and tests; forced by keep_stages)
+    // unsharp stage. Calm route: the fused level-0 collapse stores the frame and only the strip chunks that can reach the
+    // unsharp threshold run the exact blur + median path. Dense route: level-0 collapse to float planes + the exact path on
+    // every pixel. 0 = adaptive (the calm route while the share of flagged chunks seen on recent frames stays low, the dense
+    // route otherwise, probing the calm route now and then); 1 = dense always (forced by keep_stages); 2 = calm always.
     int unsharp_mode = 0;
+    double calm_share = 0.0;                 // running share of flagged strip chunks on the calm route
+    unsigned route_tick = 0;
     int mm_pitch = 0;                        // blocks per row of the clamp-excess table, padded
     size_t mm_stride = 0;
     unsigned long long* d_calm_total = nullptr;      // flagged strip chunks since the last stats read
-    uint64_t calm_chunks_total = 0;
+    unsigned long long* d_probe_total = nullptr;     // sink of the statistic-only scans
+    uint64_t calm_chunks_total = 0, dense_chunks_total = 0;
 
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
@@ -141,14 +154,46 @@ void free_chunk(poppy_cuda_ctx* c) {
         cudaFree(l.d_tile_cnt); cudaFree(l.d_tile_off); cudaFree(l.d_tile_list); cudaFree(l.d_overflow);
         cudaFree(l.d_warped); cudaFree(l.d_mask0); cudaFree(l.d_g); cudaFree(l.d_o);
         cudaFree(l.d_excess); cudaFree(l.d_block_dev); cudaFree(l.d_block_flags); cudaFree(l.d_chunk_flags); cudaFree(l.d_tile_flags); cudaFree(l.d_calm_counts);
-        cudaFreeHost(l.h_fp); cudaFreeHost(l.h_tri);
-        cudaStream_t st = l.stream; cudaEvent_t e1 = l.ev_staged, e2 = l.ev_done;
+        cudaFreeHost(l.h_fp); cudaFreeHost(l.h_tri); cudaFreeHost(l.h_calm_counts);
+        cudaStream_t st = l.stream; cudaEvent_t e1 = l.ev_staged, e2 = l.ev_done, e3 = l.ev_calm;
         l = poppy_cuda_ctx::Lane();
-        l.stream = st; l.ev_staged = e1; l.ev_done = e2;
+        l.stream = st; l.ev_staged = e1; l.ev_done = e2; l.ev_calm = e3;
     }
     c->chunk = 0;
     c->n_lanes = 0;
 }
+
+// ---- TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no libcuda link dependency) ----
+static_assert(sizeof(CUtensorMap) == sizeof(TmaMap) && alignof(CUtensorMap) <= alignof(TmaMap), "TmaMap mirrors CUtensorMap");
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// planes of 32-bit elements: [n_planes][rows][pitch], box {bx, by, bz}
+bool make_plane_map(TmaMap* out, const void* base, int pitch, int rows, size_t plane_stride, size_t n_planes, int bx, int by, int bz) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)n_planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)plane_stride * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz}, es[3] = {1, 1, 1};
+    return enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(base), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+float* g_level(poppy_cuda_ctx* c, const poppy_cuda_ctx::Lane& l, int k);
+float* o_level(poppy_cuda_ctx* c, const poppy_cuda_ctx::Lane& l, int k);
 
 size_t per_frame_scratch_bytes(const poppy_cuda_ctx* c) {
     return c->padded_pixels() * 12 + (c->g_floats + c->o_floats) * 4 + (size_t)c->list_cap * 4 + (size_t)c->n_tiles * 8 +
@@ -191,17 +236,52 @@ int ensure_chunk(poppy_cuda_ctx* c) {
         CU_TRY(c, dmalloc(&l.d_chunk_flags, B * (size_t)div_up(c->w, UNSHARP_STRIP_W) * div_up(c->h, kSparseChunkRows)));
         CU_TRY(c, dmalloc(&l.d_tile_flags, B * (size_t)div_up(c->w, 128) * div_up(c->h, 32)));
         CU_TRY(c, dmalloc(&l.d_calm_counts, B));
+        CU_TRY(c, cudaMallocHost((void**)&l.h_calm_counts, B * sizeof(int)));
         CU_TRY(c, cudaMallocHost((void**)&l.h_fp, B * sizeof(FrameParams)));
         CU_TRY(c, cudaMallocHost((void**)&l.h_tri, std::max<size_t>(B * c->max_tri, 1) * 3 * sizeof(int32_t)));
     }
     c->chunk = want;
     c->n_lanes = lanes;
+    // tensor maps of every level's collapse (level k fine, level k+1 coarse); a level whose maps cannot be built keeps
+    // the per-warp staging kernel
+    for (int i = 0; i < lanes; ++i) {
+        auto& l = c->lane[i];
+        l.maps.assign(c->levels, CollapseMaps());
+        bool ok = true;
+        for (int k = 0; k < c->levels && ok; ++k) {
+            const LevelDesc &fl = c->lv[k], &cl = c->lv[k + 1];
+            CollapseMaps& m = l.maps[k];
+            if (k == 0) {
+                ok = make_plane_map(&m.fine, l.d_warped, c->pitch0(), c->h, c->padded_pixels(), 2 * B, 128, 2, 2) &&
+                     make_plane_map(&m.mask, l.d_mask0, c->pitch0(), c->h, c->padded_pixels(), B, 128, 2, 1);
+            } else {
+                // levels too small for a 128 x 2 box have no interior tile anyway; keep the box inside the tensor
+                if (fl.pitch < 128 || fl.h < 2) { m = CollapseMaps(); continue; }
+                ok = make_plane_map(&m.fine, g_level(c, l, k), fl.pitch, fl.h, fl.plane_stride, 7 * B, 128, 2, 7);
+                m.mask = m.fine;
+            }
+            if (!ok) break;
+            if (cl.pitch < 72) { m = CollapseMaps(); continue; }
+            ok = make_plane_map(&m.gc, g_level(c, l, k + 1), cl.pitch, cl.h, cl.plane_stride, 7 * B, 72, 1, 6) &&
+                 make_plane_map(&m.oc, o_level(c, l, k + 1), cl.pitch, cl.h, cl.plane_stride, 3 * B, 72, 1, 3);
+        }
+        if (!ok) l.maps.clear();
+    }
     return 0;
 }
 
 // level k block of a chunk: all frames' planes of that level are contiguous
 float* g_level(poppy_cuda_ctx* c, const poppy_cuda_ctx::Lane& l, int k) { return l.d_g + c->g_off[k] * c->chunk; }
 float* o_level(poppy_cuda_ctx* c, const poppy_cuda_ctx::Lane& l, int k) { return l.d_o + c->o_off[k] * c->chunk; }
+
+// tensor maps of level k's collapse, or null where the level has none (all-zero map = not built)
+const CollapseMaps* level_maps(const poppy_cuda_ctx::Lane& l, int k) {
+    if (k >= (int)l.maps.size()) return nullptr;
+    const CollapseMaps& m = l.maps[k];
+    bool any = false;
+    for (unsigned long long v : m.gc.v) any = any || v != 0;
+    return any ? &m : nullptr;
+}
 
 cudaEvent_t get_event(poppy_cuda_ctx* c) {
     if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
@@ -232,6 +312,29 @@ void collect_timing(poppy_cuda_ctx* c) {
     c->timed.clear();
 }
 
+// Adaptive routing of the unsharp stage (unsharp_mode 0): calm route while at most this share of the strip chunks of recent
+// frames needed (or, on the dense route, would have needed) the exact path; the dense route otherwise. On the dense route
+// every kCalmProbeEvery-th chunk also runs the calm analysis on its finished frames - a few percent of a chunk's time - so
+// that the router notices when the content calms down again. (Break-even: the calm route costs about half of the dense one
+// plus 1.4x the dense cost of whatever it flags.)
+constexpr double kCalmRouteMaxShare = 0.25;
+constexpr unsigned kCalmProbeEvery = 4;      // on the dense route: every n-th chunk also runs the (cheap) byte scan for the statistic
+
+// fold the flagged-chunk counts of finished calm-route chunks into the running share (never blocks unless `wait`)
+void harvest_calm_stats(poppy_cuda_ctx* c, bool wait) {
+    const int chunks_per_frame = div_up(c->w, UNSHARP_STRIP_W) * div_up(c->h, kSparseChunkRows);
+    for (auto& l : c->lane) {
+        if (!l.calm_pending) continue;
+        if (wait) cudaEventSynchronize(l.ev_calm);
+        else if (cudaEventQuery(l.ev_calm) != cudaSuccess) { cudaGetLastError(); continue; }
+        long long flagged = 0;
+        for (int i = 0; i < l.calm_pending; ++i) flagged += l.h_calm_counts[i];
+        const double share = (double)flagged / ((double)l.calm_pending * chunks_per_frame);
+        c->calm_share = 0.5 * c->calm_share + 0.5 * share;
+        l.calm_pending = 0;
+    }
+}
+
 int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* shape, const double* mask, const int32_t* tri_idx,
                  const int32_t* tri_off, bool chain, poppy_cuda_ctx::Lane& ln) {
     cudaStream_t st = ln.stream;
@@ -243,11 +346,8 @@ int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* s
         const int f = first + i;
         const int nt = tri_off[f + 1] - tri_off[f];
         if (nt < 0 || nt > c->max_tri) return fail(c, POPPY_CUDA_ERR_CAPACITY, "frame %d has %d triangles (max %d)", f, nt, c->max_tri);
-        const int32_t* src = tri_idx + (size_t)tri_off[f] * 3;
-        for (int j = 0; j < nt * 3; ++j)
-            if ((unsigned)src[j] >= (unsigned)c->n_points)
-                return fail(c, POPPY_CUDA_ERR_INVALID, "frame %d: vertex index %d out of range [0,%d)", f, src[j], c->n_points);
-        std::memcpy(ht + (size_t)tri_total * 3, src, (size_t)nt * 3 * sizeof(int32_t));
+        const int32_t* src = tri_idx + (size_t)tri_off[f] * 3;        // validated by poppy_cuda_render_range
+        if (nt) std::memcpy(ht + (size_t)tri_total * 3, src, (size_t)nt * 3 * sizeof(int32_t));
         FrameParams& p = hp[i];
         p.shape = shape[f];
         p.one_minus_r = (float)(1.0 - (double)p.shape);
@@ -302,28 +402,62 @@ int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* s
     }
     for (int k = L - 1; k >= 1; --k) {
         Scope s(c, KC_COLLAPSE, st);
-        launch_collapse(st, g_level(c, ln, k), c->lv[k], g_level(c, ln, k + 1), o_level(c, ln, k + 1), c->lv[k + 1], o_level(c, ln, k), nb);
+        launch_collapse(st, g_level(c, ln, k), c->lv[k], g_level(c, ln, k + 1), o_level(c, ln, k + 1), c->lv[k + 1], o_level(c, ln, k), nb,
+                        level_maps(ln, k));
     }
-    const int force_exact = (c->unsharp_mode == 1 || c->keep_stages) ? 1 : 0;
-    {   Scope s(c, KC_COLLAPSE, st);
-        launch_collapse0_emit(st, ln.d_warped, c->pitch0(), c->padded_pixels(), ln.d_mask0, c->pitch0(), c->padded_pixels(), w, h,
-                              g_level(c, ln, 1), o_level(c, ln, 1), c->lv[1], ln.d_fp, c->d_frames, c->frame_bytes(), ln.d_excess,
-                              c->mm_pitch, c->mm_stride, nb);
-    }
-    {   Scope s(c, KC_CALM, st);
-        c->launches += 2;       // byte scan + block flags + chunk flags
-        launch_calm_analysis(st, c->d_frames, c->frame_bytes(), ln.d_fp, ln.d_excess, c->mm_pitch, c->mm_stride, w, h, nb,
-                             kSparseChunkRows, ln.d_block_dev, ln.d_block_flags, ln.d_chunk_flags, ln.d_tile_flags, ln.d_calm_counts, c->d_calm_total,
-                             force_exact);
-        c->calm_chunks_total += (uint64_t)nb * div_up(w, UNSHARP_STRIP_W) * div_up(h, kSparseChunkRows);
-    }
-    {   Scope s(c, KC_COLLAPSE, st);
-        launch_collapse0(st, ln.d_warped, c->pitch0(), c->padded_pixels(), ln.d_mask0, c->pitch0(), c->padded_pixels(), w, h, g_level(c, ln, 1),
-                         o_level(c, ln, 1), c->lv[1], o_level(c, ln, 0), c->lv[0], nb, ln.d_tile_flags);
-    }
-    {   Scope s(c, KC_UNSHARP, st);
-        launch_unsharp_store(st, o_level(c, ln, 0), c->lv[0], ln.d_fp, c->d_frames, c->frame_bytes(), nb, kSparseChunkRows,
-                             ln.d_chunk_flags);
+    // ---- level 0: collapse + unsharp_mask + 8-bit store, by one of two bit-identical routes ---------------------------
+    const int chunks_per_frame = div_up(w, UNSHARP_STRIP_W) * div_up(h, kSparseChunkRows);
+    harvest_calm_stats(c, false);
+    bool calm_route;
+    if (c->keep_stages || c->unsharp_mode == 1) calm_route = false;
+    else if (c->unsharp_mode == 2) calm_route = true;
+    else calm_route = c->calm_share <= kCalmRouteMaxShare;
+    if (calm_route) {
+        {   Scope s(c, KC_COLLAPSE, st);
+            launch_collapse0_emit(st, ln.d_warped, c->pitch0(), c->padded_pixels(), ln.d_mask0, c->pitch0(), c->padded_pixels(), w, h,
+                                  g_level(c, ln, 1), o_level(c, ln, 1), c->lv[1], ln.d_fp, c->d_frames, c->frame_bytes(), ln.d_excess,
+                                  c->mm_pitch, c->mm_stride, nb, level_maps(ln, 0));
+        }
+        {   Scope s(c, KC_CALM, st);
+            c->launches += 2;       // byte scan + block flags + chunk flags
+            launch_calm_analysis(st, c->d_frames, c->frame_bytes(), ln.d_fp, ln.d_excess, c->mm_pitch, c->mm_stride, w, h, nb,
+                                 kSparseChunkRows, ln.d_block_dev, ln.d_block_flags, ln.d_chunk_flags, ln.d_tile_flags, ln.d_calm_counts,
+                                 c->d_calm_total, 0);
+            c->calm_chunks_total += (uint64_t)nb * chunks_per_frame;
+        }
+        if (ln.calm_pending) { CU_TRY(c, cudaEventSynchronize(ln.ev_calm)); harvest_calm_stats(c, false); }
+        CU_TRY(c, cudaMemcpyAsync(ln.h_calm_counts, ln.d_calm_counts, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU_TRY(c, cudaEventRecord(ln.ev_calm, st));
+        ln.calm_pending = nb;
+        {   Scope s(c, KC_COLLAPSE, st);
+            launch_collapse0(st, ln.d_warped, c->pitch0(), c->padded_pixels(), ln.d_mask0, c->pitch0(), c->padded_pixels(), w, h,
+                             g_level(c, ln, 1), o_level(c, ln, 1), c->lv[1], o_level(c, ln, 0), c->lv[0], nb, ln.d_tile_flags, level_maps(ln, 0));
+        }
+        {   Scope s(c, KC_UNSHARP, st);
+            launch_unsharp_store(st, o_level(c, ln, 0), c->lv[0], ln.d_fp, c->d_frames, c->frame_bytes(), nb, kSparseChunkRows,
+                                 ln.d_chunk_flags);
+        }
+    } else {
+        {   Scope s(c, KC_COLLAPSE, st);
+            launch_collapse0(st, ln.d_warped, c->pitch0(), c->padded_pixels(), ln.d_mask0, c->pitch0(), c->padded_pixels(), w, h,
+                             g_level(c, ln, 1), o_level(c, ln, 1), c->lv[1], o_level(c, ln, 0), c->lv[0], nb, nullptr, level_maps(ln, 0));
+        }
+        {   Scope s(c, KC_UNSHARP, st);
+            launch_unsharp_store(st, o_level(c, ln, 0), c->lv[0], ln.d_fp, c->d_frames, c->frame_bytes(), nb, 0, nullptr);
+        }
+        c->dense_chunks_total += (uint64_t)nb * chunks_per_frame;
+        if (c->unsharp_mode == 0 && !c->keep_stages && (++c->route_tick % kCalmProbeEvery) == 0 && !ln.calm_pending) {
+            // statistic only: the byte scan of the finished frames (no clamp-excess information on this route)
+            Scope s(c, KC_CALM, st);
+            c->launches += 2;
+            CU_TRY(c, cudaMemsetAsync(ln.d_excess, 0, (size_t)nb * 3 * c->mm_stride, st));
+            launch_calm_analysis(st, c->d_frames, c->frame_bytes(), ln.d_fp, ln.d_excess, c->mm_pitch, c->mm_stride, w, h, nb,
+                                 kSparseChunkRows, ln.d_block_dev, ln.d_block_flags, ln.d_chunk_flags, ln.d_tile_flags, ln.d_calm_counts,
+                                 c->d_probe_total, 0);
+            CU_TRY(c, cudaMemcpyAsync(ln.h_calm_counts, ln.d_calm_counts, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU_TRY(c, cudaEventRecord(ln.ev_calm, st));
+            ln.calm_pending = nb;
+        }
     }
     if (chain) {
         Scope s(c, KC_MISC, st);
@@ -356,7 +490,7 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
     *out = nullptr;
     if (width <= 0 || height <= 0 || width >= 32767 || height >= 32767)
         return fail(nullptr, POPPY_CUDA_ERR_INVALID, "frame size %dx%d out of range (cv::remap needs < 32767)", width, height);
-    if (pyramid_levels < 1 || max_points < 3 || max_triangles < 1 || max_batch_frames < 1)
+    if (pyramid_levels < 1 || max_points < 1 || max_triangles < 1 || max_batch_frames < 1)
         return fail(nullptr, POPPY_CUDA_ERR_INVALID, "pyramid_levels/max_points/max_triangles/max_batch_frames out of range");
     int ndev = poppy_cuda_device_count();
     if (ndev <= 0) return fail(nullptr, POPPY_CUDA_ERR_NO_DEVICE, "no CUDA device: the morph renderer has no CPU fallback");
@@ -380,6 +514,7 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
         CR_TRY(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         CR_TRY(cudaEventCreateWithFlags(&l.ev_staged, cudaEventDisableTiming));
         CR_TRY(cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming));
+        CR_TRY(cudaEventCreateWithFlags(&l.ev_calm, cudaEventDisableTiming));
     }
     // pyramid geometry: (n+1)/2 per level, 1x1 levels repeat (cv::pyrDown, pyramids.cpp:1260-1303)
     c->lv.resize(pyramid_levels + 1);
@@ -406,6 +541,7 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
     }
     c->mm_pitch = (div_up(width, CALM_BLOCK_W) + 15) & ~15;
     c->mm_stride = (size_t)c->mm_pitch * div_up(height, CALM_BLOCK_H);
+    CR_TRY(dmalloc(&c->d_probe_total, (size_t)1));
     CR_TRY(dmalloc(&c->d_calm_total, (size_t)1));
     CR_TRY(cudaMemset(c->d_calm_total, 0, sizeof(unsigned long long)));
     const size_t px = c->pixels();
@@ -445,13 +581,13 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
     collect_timing(c);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     free_chunk(c);
-    cudaFree(c->d_src_stage); cudaFree(c->d_mbasis);
+    cudaFree(c->d_src_stage); cudaFree(c->d_mbasis); cudaFree(c->d_stage_u8); cudaFree(c->d_stage_f32);
     for (int i = 0; i < 3; ++i) {
         if (c->t_src[i]) cudaDestroyTextureObject(c->t_src[i]);
         if (c->a_src[i]) cudaFreeArray(c->a_src[i]);
     }
     cudaFree(c->d_pts1_raw); cudaFree(c->d_pts2_raw); cudaFree(c->d_pts1); cudaFree(c->d_pts2); cudaFree(c->d_morphed);
-    cudaFree(c->d_frames); cudaFree(c->d_sum); cudaFree(c->d_calm_total);
+    cudaFree(c->d_frames); cudaFree(c->d_sum); cudaFree(c->d_calm_total); cudaFree(c->d_probe_total);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
@@ -460,6 +596,7 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
     for (auto& l : c->lane) {
         if (l.ev_staged) cudaEventDestroy(l.ev_staged);
         if (l.ev_done) cudaEventDestroy(l.ev_done);
+        if (l.ev_calm) cudaEventDestroy(l.ev_calm);
         if (l.stream) cudaStreamDestroy(l.stream);
     }
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -503,7 +640,7 @@ int poppy_cuda_set_tile_list_capacity(poppy_cuda_ctx* c, int entries) {
 
 int poppy_cuda_set_unsharp_mode(poppy_cuda_ctx* c, int mode) {
     if (!c) return POPPY_CUDA_ERR_INVALID;
-    if (mode != 0 && mode != 1) return fail(c, POPPY_CUDA_ERR_INVALID, "unsharp mode must be 0 (calm analysis) or 1 (exact path everywhere)");
+    if (mode < 0 || mode > 2) return fail(c, POPPY_CUDA_ERR_INVALID, "unsharp mode must be 0 (adaptive), 1 (dense) or 2 (calm route)");
     c->unsharp_mode = mode;
     return 0;
 }
@@ -513,12 +650,13 @@ int poppy_cuda_unsharp_stats(poppy_cuda_ctx* c, uint64_t* chunks_exact, uint64_t
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     for (auto& l : c->lane) if (l.stream) CU_TRY(c, cudaStreamSynchronize(l.stream));
+    harvest_calm_stats(c, true);
     unsigned long long v = 0;
     CU_TRY(c, cudaMemcpy(&v, c->d_calm_total, sizeof v, cudaMemcpyDeviceToHost));
     CU_TRY(c, cudaMemset(c->d_calm_total, 0, sizeof v));
-    if (chunks_exact) *chunks_exact = v;
-    if (chunks_total) *chunks_total = c->calm_chunks_total;
-    c->calm_chunks_total = 0;
+    if (chunks_exact) *chunks_exact = v + c->dense_chunks_total;
+    if (chunks_total) *chunks_total = c->calm_chunks_total + c->dense_chunks_total;
+    c->calm_chunks_total = c->dense_chunks_total = 0;
     return 0;
 }
 
@@ -528,48 +666,73 @@ int poppy_cuda_set_stage_timing(poppy_cuda_ctx* c, int enable) {
     return 0;
 }
 
+// upload staging of the pair, allocated on first use and kept (no cudaMalloc / cudaFree per call)
+static int ensure_pair_staging(poppy_cuda_ctx* c) {
+    if (!c->d_stage_u8) CU_TRY(c, dmalloc(&c->d_stage_u8, c->frame_bytes()));
+    if (!c->d_stage_f32) CU_TRY(c, dmalloc(&c->d_stage_f32, c->pixels() * 3));
+    return 0;
+}
+
+int poppy_cuda_set_image(poppy_cuda_ctx* c, int which, const void* data, size_t step) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (!data || which < 0 || which > 2) return fail(c, POPPY_CUDA_ERR_INVALID, "bad image selector or null pointer");
+    const size_t row = (size_t)c->w * 3, grow = row * sizeof(float), trow = (size_t)c->w * 4;
+    if (step < (which == 2 ? grow : row)) return fail(c, POPPY_CUDA_ERR_INVALID, "row stride smaller than a row");
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (int rc = ensure_pair_staging(c)) return rc;
+    if (which < 2) {
+        CU_TRY(c, cudaMemcpy2DAsync(c->d_stage_u8, row, data, step, row, c->h, cudaMemcpyHostToDevice, c->stream));
+        launch_bgr_to_bgrx(c->stream, c->d_stage_u8, c->d_src_stage, c->w, c->h);
+        CU_TRY(c, cudaMemcpy2DToArrayAsync(c->a_src[which], 0, 0, c->d_src_stage, trow, trow, c->h, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        CU_TRY(c, cudaMemcpy2DAsync(c->d_stage_f32, grow, data, step, grow, c->h, cudaMemcpyHostToDevice, c->stream));
+        launch_mask_basis(c->stream, c->d_stage_f32, c->d_mbasis, c->pitch0(), c->w, c->h);
+    }
+    c->launches++; c->class_launches[KC_MISC]++;
+    CU_TRY(c, cudaGetLastError());
+    c->have_image[which] = true;
+    c->have_pair = c->have_image[0] && c->have_image[1] && c->have_image[2];
+    return 0;
+}
+
 int poppy_cuda_set_pair(poppy_cuda_ctx* c, const uint8_t* bgr1, size_t step1, const uint8_t* bgr2, size_t step2,
                         const float* gabor, size_t gstep) {
     if (!c) return POPPY_CUDA_ERR_INVALID;
     if (!bgr1 || !bgr2 || !gabor) return fail(c, POPPY_CUDA_ERR_INVALID, "null image pointer");
-    const size_t row = (size_t)c->w * 3, grow = row * sizeof(float);
-    if (step1 < row || step2 < row || gstep < grow) return fail(c, POPPY_CUDA_ERR_INVALID, "row stride smaller than a row");
+    int rc;
+    if ((rc = poppy_cuda_set_image(c, 0, bgr1, step1)) != 0 || (rc = poppy_cuda_set_image(c, 1, bgr2, step2)) != 0 ||
+        (rc = poppy_cuda_set_image(c, 2, gabor, gstep)) != 0)
+        return rc;
+    // the host arrays may be pinned (a truly asynchronous copy) and reused by the caller right after this call
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int poppy_cuda_set_source1_from_slot(poppy_cuda_ctx* c, int slot) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (slot < 0 || slot >= c->max_frames) return fail(c, POPPY_CUDA_ERR_INVALID, "bad frame slot");
     CU_TRY(c, cudaSetDevice(c->device));
-    uint8_t* stage = nullptr;
-    float* gstage = nullptr;
-    CU_TRY(c, dmalloc(&stage, c->frame_bytes()));
-    cudaError_t e = dmalloc(&gstage, c->pixels() * 3);
-    if (e != cudaSuccess) { cudaFree(stage); return fail(c, POPPY_CUDA_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
-    int rc = 0;
-    auto run = [&]() -> int {
-        CU_TRY(c, cudaMemcpy2DAsync(stage, row, bgr1, step1, row, c->h, cudaMemcpyHostToDevice, c->stream));
-        const size_t trow = (size_t)c->w * 4;
-        launch_bgr_to_bgrx(c->stream, stage, c->d_src_stage, c->w, c->h);
-        CU_TRY(c, cudaMemcpy2DToArrayAsync(c->a_src[0], 0, 0, c->d_src_stage, trow, trow, c->h, cudaMemcpyDeviceToDevice, c->stream));
-        CU_TRY(c, cudaMemcpy2DAsync(stage, row, bgr2, step2, row, c->h, cudaMemcpyHostToDevice, c->stream));
-        launch_bgr_to_bgrx(c->stream, stage, c->d_src_stage, c->w, c->h);
-        CU_TRY(c, cudaMemcpy2DToArrayAsync(c->a_src[1], 0, 0, c->d_src_stage, trow, trow, c->h, cudaMemcpyDeviceToDevice, c->stream));
-        CU_TRY(c, cudaMemcpy2DAsync(gstage, grow, gabor, gstep, grow, c->h, cudaMemcpyHostToDevice, c->stream));
-        launch_mask_basis(c->stream, gstage, c->d_mbasis, c->pitch0(), c->w, c->h);
-        c->launches += 3; c->class_launches[KC_MISC] += 3;
-        CU_TRY(c, cudaGetLastError());
-        CU_TRY(c, cudaStreamSynchronize(c->stream));
-        return 0;
-    };
-    rc = run();
-    cudaFree(stage);
-    cudaFree(gstage);
-    if (rc == 0) c->have_pair = true;
-    return rc;
+    const size_t trow = (size_t)c->w * 4;
+    launch_bgr_to_bgrx(c->stream, c->d_frames + (size_t)slot * c->frame_bytes(), c->d_src_stage, c->w, c->h);
+    CU_TRY(c, cudaMemcpy2DToArrayAsync(c->a_src[0], 0, 0, c->d_src_stage, trow, trow, c->h, cudaMemcpyDeviceToDevice, c->stream));
+    c->launches++; c->class_launches[KC_MISC]++;
+    CU_TRY(c, cudaGetLastError());
+    c->have_image[0] = true;
+    c->have_pair = c->have_image[0] && c->have_image[1] && c->have_image[2];
+    return 0;
 }
 
 int poppy_cuda_set_points(poppy_cuda_ctx* c, const float* pts1, const float* pts2, int n) {
     if (!c) return POPPY_CUDA_ERR_INVALID;
-    if (!pts1 || !pts2 || n < 3) return fail(c, POPPY_CUDA_ERR_INVALID, "need two point sets of >= 3 points");
+    // fewer than 3 points give no triangle: like the reference (an empty Delaunay mesh) the frame is then the blend of the
+    // unwarped pair
+    if ((n > 0 && (!pts1 || !pts2)) || n < 0) return fail(c, POPPY_CUDA_ERR_INVALID, "bad point sets");
     if (n > c->max_points) return fail(c, POPPY_CUDA_ERR_CAPACITY, "%d points (max %d)", n, c->max_points);
     CU_TRY(c, cudaSetDevice(c->device));
-    CU_TRY(c, cudaMemcpyAsync(c->d_pts1_raw, pts1, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(c, cudaMemcpyAsync(c->d_pts2_raw, pts2, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (n > 0) {
+        CU_TRY(c, cudaMemcpyAsync(c->d_pts1_raw, pts1, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(c->d_pts2_raw, pts2, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    }
     launch_clip_points(c->stream, c->d_pts1_raw, c->d_pts1, n, c->w, c->h);
     launch_clip_points(c->stream, c->d_pts2_raw, c->d_pts2, n, c->w, c->h);
     c->launches += 2; c->class_launches[KC_MISC] += 2;
@@ -590,13 +753,23 @@ int poppy_cuda_render_range(poppy_cuda_ctx* c, int first_slot, int n_frames, con
     if (!c) return POPPY_CUDA_ERR_INVALID;
     if (first_slot < 0 || (chain && first_slot != 0)) return fail(c, POPPY_CUDA_ERR_INVALID, "bad first_slot %d (a chain starts at slot 0)", first_slot);
     if (!c->have_pair || !c->have_points) return fail(c, POPPY_CUDA_ERR_STATE, "set_pair and set_points must precede render");
-    if (!shape || !mask || !tri_idx || !tri_off) return fail(c, POPPY_CUDA_ERR_INVALID, "null argument");
+    if (!shape || !mask || !tri_off) return fail(c, POPPY_CUDA_ERR_INVALID, "null argument");
+    if (!tri_idx && n_frames >= 1 && tri_off[n_frames] != tri_off[0]) return fail(c, POPPY_CUDA_ERR_INVALID, "null triangle list");
     if (n_frames < 1 || first_slot + n_frames > c->max_frames)
         return fail(c, POPPY_CUDA_ERR_CAPACITY, "frames [%d, %d) exceed the ring (max %d)", first_slot, first_slot + n_frames, c->max_frames);
     CU_TRY(c, cudaSetDevice(c->device));
     if (int rc = ensure_chunk(c)) return rc;
     if (first_slot < c->copy_hi && first_slot + n_frames > c->copy_lo)      // slots with a download in flight
         CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
+    // validate every frame before anything is enqueued: a failure must not leave earlier chunks running on the lanes
+    for (int f = 0; f < n_frames; ++f) {
+        const int nt = tri_off[f + 1] - tri_off[f];
+        if (nt < 0 || nt > c->max_tri) return fail(c, POPPY_CUDA_ERR_CAPACITY, "frame %d has %d triangles (max %d)", f, nt, c->max_tri);
+        const int32_t* src = tri_idx + (size_t)tri_off[f] * 3;
+        for (int j = 0; j < nt * 3; ++j)
+            if ((unsigned)src[j] >= (unsigned)c->n_points)
+                return fail(c, POPPY_CUDA_ERR_INVALID, "frame %d: vertex index %d out of range [0,%d)", f, src[j], c->n_points);
+    }
     collect_timing(c);
     std::fill(c->class_ms, c->class_ms + KC_COUNT, 0.f);
     std::fill(c->class_launches, c->class_launches + KC_COUNT, 0ull);
@@ -609,7 +782,15 @@ int poppy_cuda_render_range(poppy_cuda_ctx* c, int first_slot, int n_frames, con
     int k = 0;
     for (int first = 0; first < n_frames; first += B, ++k) {
         const int nb = std::min(B, n_frames - first);
-        if (int rc = render_chunk(c, first_slot, first, nb, shape, mask, tri_idx, tri_off, chain != 0, c->lane[k % lanes])) return rc;
+        if (int rc = render_chunk(c, first_slot, first, nb, shape, mask, tri_idx, tri_off, chain != 0, c->lane[k % lanes])) {
+            // a CUDA failure mid-render: still join the lanes so that later syncs / frees cover what was enqueued
+            for (int i = 0; i < lanes; ++i) {
+                cudaEventRecord(c->lane[i].ev_done, c->lane[i].stream);
+                cudaStreamWaitEvent(c->stream, c->lane[i].ev_done, 0);
+            }
+            cudaEventRecord(c->ev_end, c->stream);
+            return rc;
+        }
     }
     for (int i = 0; i < lanes; ++i) {
         CU_TRY(c, cudaEventRecord(c->lane[i].ev_done, c->lane[i].stream));

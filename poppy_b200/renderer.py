@@ -43,7 +43,7 @@ class MorphRenderer:
             self._check(self._lib.poppy_cuda_set_stage_timing(self._ctx, 1))
 
     def set_unsharp_mode(self, mode: int):
-        """0: calm analysis (exact blur + median only where unsharp_mask() can change a pixel); 1: exact path everywhere."""
+        """0: adaptive; 1: dense (exact blur + median on every pixel); 2: calm route (exact path only on flagged chunks)."""
         self._check(self._lib.poppy_cuda_set_unsharp_mode(self._ctx, int(mode)))
 
     def unsharp_stats(self) -> tuple:
