@@ -9,6 +9,10 @@ A *step* is one pass of the hot path over one batch of synthetic input: `--frame
 per-frame triangle lists prepared beforehand. Default workload: BASELINE.json configs[3] — synthetic 3840x2160
 pair, 20k matched points (~40k triangles), 6-level pyramid; 600 phases per step and rank.
 
+    python bench.py --workload 1080p|4k|8k                     # the other points of the metric (default 4k = configs[3])
+    python bench.py --workload 8k --total-frames 2400 --gpus N   # configs[4]: 2,400 8K phases sharded over N ranks (strong scaling)
+    python bench.py --mode chain                                # configs[0]: the reference demo pair, 60 chained frames, 64 levels
+
 JSON line (rank 0):
   value       whole-job frames/s with inputs resident in HBM, device time (CUDA events on the context's stream),
               max over ranks
@@ -58,8 +62,9 @@ def ncu_traffic():
 
 
 def dominant_kernel_roofline(kern, W, H, F, chunk_frames, peak, traffic, levels=6):
-    """roofline of the kernel class with the largest share of the step, per launch: algorithmic bytes of that stage
-     / its CUDA-event launch time measured in this run."""
+    """roofline of the kernel class with the largest share of the step: algorithmic bytes of that stage per launch
+     / its CUDA-event launch time measured in this run. A class made of several per-level launches
+    is rated over the launch sequence of one chunk."""
     if not kern:
         return None
     P, lw, lh = [], W, H
@@ -68,7 +73,6 @@ def dominant_kernel_roofline(kern, W, H, F, chunk_frames, peak, traffic, levels=
         lw, lh = (lw + 1) // 2, (lh + 1) // 2
     px, mid = P[0], sum(P[1:levels])
     # compulsory bytes per frame of each kernel class as designed: every input read once, every output written once
-    # 
     alg = {
         "raster_warp": 8 * px + 8 * px / max(chunk_frames, 1),     # warped pair written; both sources read once per chunk
         "unsharp_store": 15 * px,                                   # lapBlend 32FC3 read, 8UC3 frame written
@@ -80,23 +84,19 @@ def dominant_kernel_roofline(kern, W, H, F, chunk_frames, peak, traffic, levels=
     }
     k = kern[0]
     name = k["kernel"]
-    per_chunk = {"raster_warp": 1, "unsharp_store": 1, "blend_collapse": levels + 1, "pyr_down": levels}
-    frames_per_launch = F * per_chunk[name] / k["launches_per_step"] if name in per_chunk else None
-    if name in ("blend_collapse", "pyr_down") and frames_per_launch:
-        # the class is a sequence of per-level launches: rate it over the whole sequence of one chunk
-        k = dict(k, us_per_launch=k["us_per_launch"] * per_chunk[name])
-        out_note = f"{per_chunk[name]} per-level launches of one chunk rated together"
-    else:
-        out_note = None
-    out = {"kernel": name, "us_per_launch": k["us_per_launch"], "share_of_step": k["share"]}
-    if out_note:
-        out["note"] = out_note
-    if name in alg and frames_per_launch:
-        b = alg[name] * frames_per_launch
-        ach = b / (k["us_per_launch"] * 1e-6) / 1e9
-        out.update({"algorithmic_bytes_per_launch": int(b), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak})
-    if traffic and name in traffic.get("bytes_per_frame", {}) and frames_per_launch:
-        out["traffic"] = int(traffic["bytes_per_frame"][name] * frames_per_launch)
+    chunks = max(1, -(-F // max(chunk_frames, 1)))
+    launches_per_chunk = max(1, round(k["launches_per_step"] / chunks))
+    out = {"kernel": name, "share_of_step": k["share"], "launches_per_chunk": launches_per_chunk,
+           "us_per_launch": k["us_per_launch"] * launches_per_chunk}
+    if launches_per_chunk > 1:
+        out["note"] = f"{launches_per_chunk} launches of one chunk rated together"
+    if name in alg:
+        b = alg[name] * F
+        ach = b / (k["ms_per_step"] * 1e-3) / 1e9
+        out.update({"algorithmic_bytes_per_launch": int(alg[name] * min(F, chunk_frames)), "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak})
+    if traffic and name in traffic.get("bytes_per_frame", {}):
+        out["traffic"] = int(traffic["bytes_per_frame"][name] * min(F, chunk_frames))
         out["traffic_source"] = traffic.get("source")
     return out
 
@@ -166,40 +166,154 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def reference_arm(args, wl, rank, world):
+class Job:
+    """The workload of one rank: inputs, frame schedule, and the config dict both arms print."""
+
+    def __init__(self, args, rank, world):
+        from poppy_b200 import synth, shard, host
+        self.mode = args.mode
+        self.chain = args.mode == "chain"
+        if self.chain:
+            # BASELINE.json configs[0]: images/square.png -> images/circle.png through the reference front end (blur_margin,
+            # extractor, matcher, gabor_filter): what it handed to morph_images() is the committed fixture
+            g = np.load(os.path.join(ROOT, "tests", "golden", "full", "c1.npz"))
+            self.W, self.H, self.L = int(g["width"]), int(g["height"]), int(g["levels"])
+            self.bgr1, self.bgr2, self.gabor2 = g["corrected1"], g["corrected2"], g["gabor2"]
+            self.pts1, self.pts2 = g["pts1"], g["pts2"]
+            self.F = int(g["n_frames"])
+            self.total = self.F * world                      # replicas: a chain does not shard (SURVEY.md 8(e))
+            ratio = np.array([host.chain_ratio(j, self.F) for j in range(self.F)], np.float64)
+            self.phases, self.masks = ratio.astype(np.float32), ratio
+            self.hashes = g["hashes"]
+            self.name = "config1-chain"
+            self.desc = (f"images/square.png -> images/circle.png (reference front end), {self.W}x{self.H}, {len(self.pts1)} matcher "
+                         f"points, {self.F} chained frames, {self.L}-level pyramid (BASELINE.json configs[0])")
+            self.scaling = "weak"
+            self.parallelism = f"chain replicas x{world} (a chain is a recurrence: it does not shard), no collective"
+        else:
+            wl = dict(synth.WORKLOADS[args.workload])
+            self.W, self.H, self.L = wl["w"], wl["h"], wl["levels"]
+            inp = synth.make_inputs(self.W, self.H, wl["n_points"], wl["jitter"], wl["seed"])
+            self.bgr1, self.bgr2, self.gabor2, self.pts1, self.pts2 = inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2
+            if args.total_frames:
+                self.total = args.total_frames
+                self.scaling = "strong"
+            else:
+                per_rank = args.frames or (300 if args.workload == "8k" else wl["frames"])
+                self.total = per_rank * world
+                self.scaling = "weak"
+            sched = shard.phase_schedule(self.total)
+            lo, hi = shard.phase_range(rank, world, self.total)
+            self.phases = np.ascontiguousarray(sched[lo:hi])
+            self.masks = self.phases.astype(np.float64)
+            self.F = hi - lo
+            self.name = args.workload
+            cfg = {"1080p": "the 1080p point of the metric", "4k": "BASELINE.json configs[3]", "8k": "BASELINE.json configs[4]"}[args.workload]
+            self.desc = (f"synthetic {self.W}x{self.H} BGR pair, {wl['n_points']}+4 matched points, {self.L}-level pyramid, "
+                         f"{self.total} independent phases over {world} rank(s) ({cfg})")
+            self.parallelism = f"phase-sharded x{world}, no collective"
+        self.frame_bytes = self.W * self.H * 3
+        # frames resident in the HBM ring at once: the whole shard where it fits (8K: 300-frame slices, 30 GB)
+        cap = args.ring or (300 if self.W * self.H > 3840 * 2160 else 1 << 30)
+        self.ring = max(1, min(self.F, cap))
+        self.slices = [(a, min(a + self.ring, self.F)) for a in range(0, self.F, self.ring)]
+
+    def config(self):
+        return {"workload": self.desc,
+                "mode": "chain (frame j sources frame j-1, reference src/poppy.hpp:177-243)" if self.chain
+                        else "direct (independent phases, reference '-f 1 -p s')",
+                "total_frames_per_step": self.total, "parallelism": self.parallelism,
+                "l2_policy": "inputs larger than L2: every frame streams its scratch (>1 GB at 4K) through HBM; consecutive frames "
+                             "write different ring slots",
+                "timing": "CUDA events on the renderer's stream, max over ranks"}
+
+
+def _kproc_worker(q, path, w, h, levels, phases):
+    """One process of the K-process CPU baseline: the reference library on one OpenCV thread."""
+    try:
+        sys.path.insert(0, ROOT)
+        from oracle import ref
+        d = np.load(path)
+        ref.set_threads(1)
+        ref.morph_images(d["bgr1"], d["bgr2"], d["gabor2"], d["pts1"], d["pts2"], 0.5, 0.5, levels)      # warm-up
+        t0 = time.perf_counter()
+        for s in phases:
+            ref.morph_images(d["bgr1"], d["bgr2"], d["gabor2"], d["pts1"], d["pts2"], float(s), float(s), levels)
+        q.put((len(phases), time.perf_counter() - t0))
+    except Exception as e:          # pragma: no cover
+        q.put((0, repr(e)))
+
+
+def kprocess_baseline(job, procs, frames_per_proc=1):
+    """Best case of the reference on the box: K independent single-threaded processes over disjoint
+    phases. Returns frames/s over the slowest process."""
+    import multiprocessing as mp
+    import tempfile
+    ctx = mp.get_context("spawn")
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "inputs.npz")
+        np.savez(path, bgr1=job.bgr1, bgr2=job.bgr2, gabor2=job.gabor2, pts1=job.pts1, pts2=job.pts2)
+        q = ctx.Queue()
+        ps = []
+        for i in range(procs):
+            ph = [float(job.phases[(7 + 13 * (i * frames_per_proc + j)) % job.F]) for j in range(frames_per_proc)]
+            ps.append(ctx.Process(target=_kproc_worker, args=(q, path, job.W, job.H, job.L, ph)))
+        for pr in ps:
+            pr.start()
+        res = [q.get(timeout=900) for _ in ps]
+        for pr in ps:
+            pr.join()
+    if any(n == 0 for n, _ in res):
+        return {"error": str([t for n, t in res if n == 0][:1])}
+    slowest = max(t for _, t in res)
+    return {"value": sum(n for n, _ in res) / slowest, "unit": "frames/s", "processes": procs, "threads_per_process": 1,
+            "sample": f"{frames_per_proc} frame(s) per process after one warm-up frame; rate = all frames / slowest process"}
+
+
+def reference_arm(args, rank, world):
     """The reference's own CPU implementation of the path (oracle/_ref/libpoppy_ref.so = unmodified reference
-    sources + vendored OpenCV 4.6.0), all host threads, one frame phase per step (a bounded sample)."""
+    sources + vendored OpenCV 4.6.0), all host threads; each step is a bounded sample of the workload."""
     if rank != 0:
         return
     from oracle import ref
-    from poppy_b200 import synth, shard
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpoppy_ref.so not built"}))
         return
-    inp = synth.make_inputs(wl["w"], wl["h"], wl["n_points"], wl["jitter"], wl["seed"])
-    sched = shard.phase_schedule(wl["frames"])
+    job = Job(args, 0, world)
     total = args.warmup + args.steps
-    picks = [int(round(i * (len(sched) - 1) / max(total - 1, 1))) for i in range(total)]
     times = []
-    for i, k in enumerate(picks):
-        s = float(sched[k])
-        t0 = time.perf_counter()
-        ref.morph_images(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, s, s, wl["levels"])
-        dt = time.perf_counter() - t0
-        if i >= args.warmup:
-            times.append(dt)
-    fps = len(times) / sum(times)
+    if job.chain:
+        per_step = job.F
+        for i in range(total):
+            t0 = time.perf_counter()
+            ref.chain(job.bgr1, job.bgr2, job.gabor2, job.pts1, job.pts2, job.F, job.L)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        sample = f"the whole {job.F}-frame chain per step, {len(times)} steps after {args.warmup} warm-up"
+    else:
+        per_step = 1
+        picks = [int(round(i * (job.F - 1) / max(total - 1, 1))) for i in range(total)]
+        for i, k in enumerate(picks):
+            s = float(job.phases[k])
+            t0 = time.perf_counter()
+            ref.morph_images(job.bgr1, job.bgr2, job.gabor2, job.pts1, job.pts2, s, s, job.L)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        sample = f"{len(times)} frames of the workload (phases spread over [0,1]), 1 frame per step, after {args.warmup} warm-up frames"
+    fps = per_step * len(times) / sum(times)
     cores = ref.get_threads()
-    sample = f"{len(times)} frames of {wl['name']} (phases spread over [0,1]), 1 frame per step, after {args.warmup} warm-up frames"
-    print(json.dumps({
+    out = {
         "impl": "reference", "metric": "morphed frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "frames_per_step": 1, "mode": "direct"},
+        "higher_is_better": True, "scaling": job.scaling, "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic" if not job.chain else "reference demo images",
+        "config": job.config(),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }
+    if args.kprocs and not job.chain:
+        out["cpu_baseline"]["k_process"] = kprocess_baseline(job, args.kprocs)
+    print(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -209,82 +323,85 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--mode", default="direct", choices=["direct", "chain"])
     ap.add_argument("--workload", default="4k", choices=["1080p", "4k", "8k"])
-    ap.add_argument("--frames", type=int, default=0, help="frame phases per step and rank (default: workload's)")
+    ap.add_argument("--frames", type=int, default=0, help="frame phases per step and rank (weak scaling; default: workload's)")
+    ap.add_argument("--total-frames", type=int, default=0, help="frame phases per step over ALL ranks (strong scaling)")
+    ap.add_argument("--ring", type=int, default=0, help="frames resident in the HBM ring (default: the shard, 300 at 8K)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per kernel batch (0 = library default)")
+    ap.add_argument("--unsharp-mode", type=int, default=0, choices=[0, 1, 2], help="0 adaptive, 1 dense, 2 calm route")
     ap.add_argument("--cpu-frames", type=int, default=4, help="reference frames timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--kprocs", type=int, default=-1, help="processes of the K-process CPU baseline (-1: one per core up to 16, 0: skip)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-slice", type=int, default=64, help="frames per planned/rendered/downloaded slice of the e2e pipeline")
     ap.add_argument("--no-stage-pass", action="store_true",
                     help="profiling runs (under ncu): skip the per-kernel-class timing pass and the e2e leg")
     args = ap.parse_args()
-
-    from poppy_b200 import synth, shard
-    wl = dict(synth.WORKLOADS[args.workload])
-    wl["name"] = args.workload
-    if args.frames:
-        wl["frames"] = args.frames
-    if args.workload == "8k" and not args.frames:
-        wl["frames"] = 300            # 2400 8K frames (239 GB) do not fit one GPU's ring; 300 per rank do
-    wl["desc"] = (f"synthetic {wl['w']}x{wl['h']} BGR pair, {wl['n_points']}+4 matched points, {wl['levels']}-level "
-                  f"pyramid, {wl['frames']} independent phases per rank (BASELINE.json configs[3] shape)")
+    if args.kprocs < 0:
+        args.kprocs = min(os.cpu_count() or 1, 16) if args.cpu_frames > 0 and args.mode == "direct" and args.workload != "8k" else 0
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        reference_arm(args, wl, rank, world)
+        reference_arm(args, rank, world)
         return
 
     import torch
     import torch.distributed as dist
-    from poppy_b200 import build, host
+    from poppy_b200 import build, host, shard
     from poppy_b200.renderer import MorphRenderer
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the morph renderer has no CPU path")
-    if rank == 0:
-        build.build()
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist.barrier()
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()           # the other ranks load the library only after rank 0 has (re)built it
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- inputs (identical on every rank), this rank's phase range, host topology plan ---------------------------
-    F = wl["frames"]
-    W, H, L = wl["w"], wl["h"], wl["levels"]
-    inp = synth.make_inputs(W, H, wl["n_points"], wl["jitter"], wl["seed"])
-    sched_all = shard.phase_schedule(F * world)
-    lo, hi = shard.phase_range(rank, world, F * world)
-    phases = np.ascontiguousarray(sched_all[lo:hi])
-    masks = phases.astype(np.float64)
+    # ---- inputs (identical on every rank), this rank's frames, host topology plan -------------------------------
+    job = Job(args, rank, world)
+    F, W, H, L = job.F, job.W, job.H, job.L
+    phases, masks = job.phases, job.masks
     ncores = os.cpu_count() or 1
     plan_threads = max(1, ncores // world)
     t0 = time.perf_counter()
-    plan = host.SequencePlan(inp.pts1, inp.pts2, W, H, phases, chain=False, threads=plan_threads)
+    plan = host.SequencePlan(job.pts1, job.pts2, W, H, phases, chain=job.chain, threads=plan_threads)
     plan_s = time.perf_counter() - t0
 
-    r = MorphRenderer(W, H, L, len(inp.pts1), plan.max_triangles, F, device=local_rank,
+    r = MorphRenderer(W, H, L, len(job.pts1), plan.max_triangles, job.ring, device=local_rank,
                       chunk_frames=args.chunk or None)
+    r.set_unsharp_mode(args.unsharp_mode)
     # pinned host copies of the pair (source of the e2e H2D)
-    pin = lambda a: torch.from_numpy(a).pin_memory()
-    h_bgr1, h_bgr2, h_gab = pin(inp.bgr1), pin(inp.bgr2), pin(inp.gabor2)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_bgr1, h_bgr2, h_gab = pin(job.bgr1), pin(job.bgr2), pin(job.gabor2)
     r.set_pair(h_bgr1.numpy(), h_bgr2.numpy(), h_gab.numpy())
-    r.set_points(inp.pts1, inp.pts2)
+    r.set_points(job.pts1, job.pts2)
     stream = torch.cuda.ExternalStream(r.stream(), device=torch.device("cuda", local_rank))
+    # per ring slice: schedule + triangle lists rebased to the slice
+    offs = plan.tri_offsets
+    slice_args = [(phases[a:b], masks[a:b], plan.tri_idx[offs[a]:offs[b]], np.ascontiguousarray(offs[a:b + 1] - offs[a]))
+                  for a, b in job.slices]
 
-    def step():
-        r.render(phases, masks, plan.tri_idx, plan.tri_offsets, chain=False)
+    def step(checksums=None):
+        for ph, mk, ti, to in slice_args:
+            r.render(ph, mk, ti, to, chain=job.chain)
+            if checksums is not None:
+                checksums.append(r.checksum(0, len(ph)))
 
     for _ in range(args.warmup):
         step()
     r.sync()
+    r.unsharp_stats()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -300,38 +417,51 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     launches = r.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    checksum = r.checksum(0, F)
+    exact_chunks, all_chunks = r.unsharp_stats()
+    sums = []
+    if len(job.slices) > 1:
+        step(sums)                 # frames of earlier slices are gone from the ring: checksum every slice as it is rendered
+    else:
+        sums.append(r.checksum(0, F))
+    checksum = shard.combine_checksums(sums) if len(sums) > 1 else sums[0]
 
     # ---- per-kernel-class shares: one more step with CUDA-event stage timing -------------------------------------
     stage, stage_total_ms = {}, None
     if not args.no_stage_pass:
         r._check(r._lib.poppy_cuda_set_stage_timing(r._ctx, 1))
-        step()
-        stage = r.stage_times()
-        stage_total_ms = r.last_render_ms()
+        acc = {}
+        stage_total_ms = 0.0
+        for ph, mk, ti, to in slice_args:
+            r.render(ph, mk, ti, to, chain=job.chain)
+            for k, v in r.stage_times().items():
+                a = acc.setdefault(k, {"ms": 0.0, "launches": 0})
+                a["ms"] += v["ms"]; a["launches"] += v["launches"]
+            stage_total_ms += r.last_render_ms()
+        stage = acc
         r._check(r._lib.poppy_cuda_set_stage_timing(r._ctx, 0))
 
     # ---- e2e: the public-API path with host buffers --------------------------------------------------------------
-    ring_frames = min(F, max(64, args.e2e_slice))        # pinned host ring: at least one slice
-    h_ring = torch.empty((ring_frames, H, W, 3), dtype=torch.uint8).pin_memory()
-    frame_bytes = H * W * 3
+    ring_frames = job.ring
+    host_ring = min(ring_frames, max(64, args.e2e_slice))      # pinned host ring: at least one slice
+    h_ring = torch.empty((host_ring, H, W, 3), dtype=torch.uint8).pin_memory()
+    frame_bytes = job.frame_bytes
     e2e_times, e2e_parts = [], None
     barrier()
     # The sequence streams through the renderer slice by slice: a planner thread triangulates slice k+1 on the host
     # cores while slice k renders and slice k-1 is copied to pinned memory (copy stream) - the reference's frame loop
-    # (src/poppy.hpp:172-243) with its three stages overlapped instead of run back to back.
+    # (src/poppy.hpp:172-243) with its three stages overlapped instead of run back to back. A chain is one slice: its
+    # point recurrence is planned ahead of the render, its frames leave in order afterwards.
     import queue
-    import threading
-    slice_frames = max(1, min(F, args.e2e_slice))
+    slice_frames = F if job.chain else max(1, min(F, args.e2e_slice, ring_frames))
     slices = [(a, min(a + slice_frames, F)) for a in range(0, F, slice_frames)]
-    for it in range(0 if args.no_stage_pass else max(args.e2e_steps, 1) + 1):
+    for it in range(0 if args.no_stage_pass or args.e2e_steps <= 0 else args.e2e_steps + 1):
         plans = queue.Queue(maxsize=3)
         plan_busy = [0.0]
 
         def planner():
             for a, b in slices:
                 t0 = time.perf_counter()
-                p = host.SequencePlan(inp.pts1, inp.pts2, W, H, phases[a:b], chain=False, threads=plan_threads)
+                p = host.SequencePlan(job.pts1, job.pts2, W, H, phases[a:b], chain=job.chain, threads=plan_threads)
                 plan_busy[0] += time.perf_counter() - t0
                 plans.put((a, b, p))
 
@@ -339,15 +469,20 @@ def main():
         th = threading.Thread(target=planner, daemon=True)
         th.start()
         r.set_pair(h_bgr1.numpy(), h_bgr2.numpy(), h_gab.numpy())
-        r.set_points(inp.pts1, inp.pts2)
+        r.set_points(job.pts1, job.pts2)
         t_c = time.perf_counter()
+        dev_slot = 0
         for _ in slices:
             a, b, p = plans.get()
-            r.render(phases[a:b], masks[a:b], p.tri_idx, p.tri_offsets, chain=False, first_slot=a)
-            slot = a % ring_frames
-            if slot + (b - a) > ring_frames:
-                slot = 0
-            r.download_async(a, b - a, h_ring.data_ptr() + slot * frame_bytes, W * 3, frame_bytes)
+            n = b - a
+            if dev_slot + n > ring_frames:
+                dev_slot = 0
+            r.render(phases[a:b], masks[a:b], p.tri_idx, p.tri_offsets, chain=job.chain, first_slot=dev_slot)
+            # frames leave through the pinned host ring in pieces of at most its size
+            for c0 in range(0, n, host_ring):
+                cn = min(host_ring, n - c0)
+                r.download_async(dev_slot + c0, cn, h_ring.data_ptr(), W * 3, frame_bytes)
+            dev_slot += n
             p.close()
         r.sync()
         t_d = time.perf_counter()
@@ -355,6 +490,7 @@ def main():
         if it > 0:        # first pass is warm-up
             e2e_times.append(t_d - t_a)
             e2e_parts = {"total_s": t_d - t_a, "h2d_s": t_c - t_a, "planner_busy_s": plan_busy[0], "plan_threads": plan_threads,
+                         "planner_frames_per_s_per_core": F / max(plan_busy[0], 1e-9) / plan_threads,
                          "slice_frames": slice_frames, "slices": len(slices)}
     e2e_s = statistics.median(e2e_times) if e2e_times else float("inf")
 
@@ -362,44 +498,47 @@ def main():
     # (src/poppy.hpp:215: images, points and ratios in, dst and morphedPoints out; every call uploads the pair,
     # triangulates on ONE host thread, renders one frame and downloads it)
     single_call = None
-    if rank == 0 and world == 1 and not args.no_stage_pass and args.e2e_steps > 0:
+    if rank == 0 and world == 1 and not args.no_stage_pass and args.e2e_steps > 0 and not job.chain:
         from poppy_b200 import api
         api.Settings.instance().pyramid_levels = L
         ts = []
         for k in range(5):
             sk = float(phases[(k * 131) % F])
             t0 = time.perf_counter()
-            api.morph_images(inp.bgr1, inp.bgr2, inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, sk, sk)
+            api.morph_images(job.bgr1, job.bgr2, job.bgr1, job.bgr2, job.gabor2, job.pts1, job.pts2, sk, sk)
             ts.append(time.perf_counter() - t0)
         api.release()
         single_call = {"value": 1.0 / statistics.median(ts[1:]), "unit": "frames/s",
                        "what": "poppy_b200.api.morph_images() called once per frame (pair H2D + single-thread Delaunay + "
                                "render + D2H per call), the reference's own calling pattern"}
-    h2d_bytes = inp.bgr1.nbytes + inp.bgr2.nbytes + inp.gabor2.nbytes + inp.pts1.nbytes + inp.pts2.nbytes + \
+    h2d_bytes = job.bgr1.nbytes + job.bgr2.nbytes + job.gabor2.nbytes + job.pts1.nbytes + job.pts2.nbytes + \
         plan.tri_idx.nbytes + plan.tri_offsets.nbytes + phases.nbytes + masks.nbytes
     d2h_bytes = F * frame_bytes
 
     # ---- reduce over ranks ---------------------------------------------------------------------------------------
+    frames_all = F
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s = float(t[0]), float(t[1])
-        l = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        l = torch.tensor([launches, F, exact_chunks, all_chunks], dtype=torch.int64, device="cuda")
         dist.all_reduce(l, op=dist.ReduceOp.SUM)
-        launches = int(l[0])
-        sums = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(sums, torch.tensor([checksum & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda"))
-        checksum_all = shard.combine_checksums([int(s[0]) for s in sums])
+        launches, frames_all, exact_chunks, all_chunks = (int(v) for v in l)
+        gsums = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(gsums, torch.tensor([checksum & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda"))
+        checksum_all = shard.combine_checksums([int(v[0]) for v in gsums])
     else:
         checksum_all = shard.combine_checksums([checksum & 0x7FFFFFFFFFFFFFFF])
 
     if rank == 0:
-        total_frames = F * world * args.steps
+        total_frames = frames_all * args.steps
         fps = total_frames / (dev_ms / 1000.0)
         alg = algorithmic_bytes_per_frame(W, H, L)
         peak, peak_src = measured_peaks()
-        traffic = ncu_traffic()
-        chunk_used = args.chunk or 32
+        traffic = ncu_traffic() if (W, H, L) == (3840, 2160, 6) else None      # the committed capture is of configs[3]
+        chunk_used = args.chunk or min(32, job.ring)
+        if job.chain:
+            chunk_used = 1
         achieved = alg * (fps / world) / 1e9            # per GPU
         kern = []
         tot = sum(v["ms"] for v in stage.values()) or 1.0
@@ -409,13 +548,10 @@ def main():
                              "launches_per_step": v["launches"], "us_per_launch": round(1000 * v["ms"] / v["launches"], 2)})
         out = {
             "metric": "morphed frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "mode": "direct (independent phases, reference '-f 1 -p s')",
-                       "frames_per_step_per_gpu": F, "parallelism": f"phase-sharded x{world}, no collective",
-                       "l2_policy": "inputs larger than L2: each step streams >100 GB through HBM scratch + frame ring",
-                       "timing": "CUDA events on the renderer's stream, max over ranks"},
-            "e2e": {"value": F * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_bytes),
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": job.scaling,
+            "vs_baseline": None, "dtype": "u8/f32", "data": "reference demo images" if job.chain else "synthetic",
+            "config": job.config(),
+            "e2e": {"value": frames_all / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "breakdown": e2e_parts, "single_call": single_call,
                     "what": "H2D pair/points + per slice: host Delaunay planning (threads), H2D triangles, render, D2H of every frame to "
                             "pinned memory; the three stages of consecutive slices overlap"},
@@ -430,21 +566,41 @@ def main():
                          "algorithmic_bytes_per_frame": alg, "kernels": kern,
                          "stage_timed_step_ms": stage_total_ms},
             "clocks": clocks,
-            "host_plan_s": plan_s, "frames_checksum": f"{checksum_all:016x}",
+            "unsharp": {"mode": ["adaptive", "dense", "calm"][args.unsharp_mode],
+                        "exact_chunk_share": (exact_chunks / all_chunks) if all_chunks else None,
+                        "what": "share of 120x24-pixel strip chunks of the timed frames that ran the exact GaussianBlur + medianBlur "
+                                "path of unsharp_mask(); the rest is provably untouched by it (see DESIGN.md)"},
+            "host_plan": {"seconds": plan_s, "threads": plan_threads, "frames_per_s": F / plan_s,
+                          "frames_per_s_per_core": F / plan_s / plan_threads},
+            "frames_checksum": f"{checksum_all:016x}",
         }
         # ---- CPU baseline + parity on the sampled frames (rank 0, N=1 only) --------------------------------------
         if world == 1 and args.cpu_frames > 0:
             from oracle import ref
-            if ref.available():
-                idx = [int(round(i * (F - 1) / max(args.cpu_frames - 1, 1))) for i in range(args.cpu_frames)]
-                ref.morph_images(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, 0.5, 0.5, L)   # warm-up
+            if not ref.available():
+                out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference",
+                                       "sample": "oracle/_ref not built"}
+            elif job.chain:
+                t0 = time.perf_counter()
+                want, _ = ref.chain(job.bgr1, job.bgr2, job.gabor2, job.pts1, job.pts2, F, L)
+                dt = time.perf_counter() - t0
+                got = r.download(0, F)
+                d = np.abs(got.astype(np.int16) - np.asarray(want).astype(np.int16))
+                out["cpu_baseline"] = {"value": F / dt, "unit": "frames/s", "cores": ref.get_threads(), "kind": "reference",
+                                       "sample": f"the whole {F}-frame chain, unmodified reference frame recurrence on all host threads"}
+                out["parity_vs_reference"] = {"frames": F, "differing_bytes": int((d != 0).sum()), "max_abs": int(d.max()),
+                                              "min_fraction_within_1": float((d <= 1).mean())}
+            else:
+                last_a, last_b = job.slices[-1]                   # frames still resident in the ring
+                idx = [last_a + int(round(i * (last_b - last_a - 1) / max(args.cpu_frames - 1, 1))) for i in range(args.cpu_frames)]
+                ref.morph_images(job.bgr1, job.bgr2, job.gabor2, job.pts1, job.pts2, 0.5, 0.5, L)   # warm-up
                 times, worst, diff_bytes, within1 = [], 0, 0, 1.0
                 for k in idx:
-                    s = float(phases[k])
+                    s_ = float(phases[k])
                     t0 = time.perf_counter()
-                    want, _ = ref.morph_images(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, s, s, L)
+                    want, _ = ref.morph_images(job.bgr1, job.bgr2, job.gabor2, job.pts1, job.pts2, s_, s_, L)
                     times.append(time.perf_counter() - t0)
-                    got = r.download(k, 1)[0]
+                    got = r.download(k - last_a, 1)[0]
                     d = np.abs(got.astype(np.int16) - want.astype(np.int16))
                     worst = max(worst, int(d.max())); diff_bytes += int((d != 0).sum())
                     within1 = min(within1, float((d <= 1).mean()))
@@ -454,9 +610,9 @@ def main():
                                                  "unmodified reference morph_images() on all host threads"}
                 out["parity_vs_reference"] = {"frames": len(idx), "differing_bytes": diff_bytes, "max_abs": worst,
                                               "min_fraction_within_1": within1}
-            else:
-                out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference",
-                                       "sample": "oracle/_ref not built"}
+                if args.kprocs:
+                    r.close()               # give the host memory back before K processes load the pair
+                    out["cpu_baseline"]["k_process"] = kprocess_baseline(job, args.kprocs)
         print(json.dumps(out))
     r.close()
     if world > 1:

@@ -116,7 +116,8 @@ int poppy_cuda_render(poppy_cuda_ctx* ctx, int n_frames, const float* shape_rati
 /* Same, into ring slots [first_slot, first_slot + n_frames): frame i of the call (arrays indexed from 0) lands in slot
  * first_slot + i. Lets a caller stream a long sequence through the ring slice by slice - plan slice k+1 on the host
  * while slice k renders and slice k-1 downloads (the frame loop of src/poppy.hpp:172-243 with the writer hand-off
- * overlapped). chain == 1 requires first_slot == 0. */
+ * overlapped). With chain == 1 and first_slot > 0 the call continues the chain of the previous call, which must have ended
+ * at slot first_slot - 1 (a long chain rendered slice by slice). */
 int poppy_cuda_render_range(poppy_cuda_ctx* ctx, int first_slot, int n_frames, const float* shape_ratio,
                             const double* mask_ratio, const int32_t* tri_idx, const int32_t* tri_offsets, int chain);
 
@@ -125,6 +126,16 @@ int poppy_cuda_render_range(poppy_cuda_ctx* ctx, int first_slot, int n_frames, c
  * held up; a render of slots with a download pending waits for it). Asynchronous if dst is pinned;
  * poppy_cuda_sync() before reading. */
 int poppy_cuda_download(poppy_cuda_ctx* ctx, int first, int count, uint8_t* dst, size_t step, size_t frame_stride);
+
+/* poppy_cuda_download that also returns a ticket; poppy_cuda_download_wait(ticket) blocks until that copy (and every earlier
+ * one) has landed, without waiting for renders or later downloads. wait may be called from another host thread (the writer
+ * hand-off, include/poppy_host.h). At most 64 tickets may be outstanding. */
+int poppy_cuda_download_async(poppy_cuda_ctx* ctx, int first, int count, uint8_t* dst, size_t step, size_t frame_stride,
+                              uint64_t* ticket);
+int poppy_cuda_download_wait(poppy_cuda_ctx* ctx, uint64_t ticket);
+/* Page-locked host memory for download targets (asynchronous copies need it). */
+int poppy_cuda_alloc_pinned(size_t bytes, void** out);
+void poppy_cuda_free_pinned(void* p);
 
 /* morphedPoints of frame `frame` of the last render (n x 2 float) — the out-parameter of morph_images. */
 int poppy_cuda_get_morphed_points(poppy_cuda_ctx* ctx, int frame, float* xy);

@@ -58,6 +58,49 @@ int poppy_morph_images(poppy_cuda_ctx* ctx, const uint8_t* corrected1, size_t st
                        const float* src_points2_xy, int n, double shape_ratio, double mask_ratio, uint8_t* dst_bgr,
                        size_t dst_step, float* morphed_xy);
 
+/* ---- writer hand-off (reference src/poppy.hpp:219 `output.write(morphed)`; cv::VideoWriter src/poppy.cpp:249) -----------
+ * A ring of page-locked frame buffers between the GPU frame ring and the caller's encoder. submit() enqueues the download
+ * of rendered ring slots and returns (it only blocks while all `ring_frames` buffers are in flight); a delivery thread
+ * waits for each copy and calls `write` strictly in frame order; with workers > 0 a thread pool first runs `convert` on
+ * each frame (in place, any order). `write` / `convert` receive the frame index, the BGR pixels and their row stride. */
+typedef struct poppy_host_writer poppy_host_writer;
+typedef void (*poppy_write_fn)(void* user, int frame_index, uint8_t* bgr, int width, int height, size_t step);
+int poppy_host_writer_create(poppy_host_writer** out, poppy_cuda_ctx* ctx, int ring_frames, poppy_write_fn write,
+                             poppy_write_fn convert /* may be NULL */, int workers, void* user);
+/* frames of ring slots [first_slot, first_slot + count) become frames first_frame_index.. of the output sequence */
+int poppy_host_writer_submit(poppy_host_writer* w, int first_slot, int count, int first_frame_index);
+int poppy_host_writer_flush(poppy_host_writer* w);          /* returns once every submitted frame has been written */
+void poppy_host_writer_destroy_cuda(poppy_host_writer* w);  /* flushes, joins the threads, frees the ring */
+
+/* The same machinery over a caller-supplied transport (tests run it without a GPU; another source of frames can reuse it). */
+typedef struct poppy_host_writer_io {
+    void* user;
+    int (*download)(void* user, int slot, uint8_t* dst, size_t step, uint64_t* ticket);   /* start copying a slot */
+    int (*wait)(void* user, uint64_t ticket);                                             /* may be NULL: copies are synchronous */
+    int (*alloc)(void* user, size_t bytes, void** out);
+    void (*release)(void* user, void* p);
+    void (*write)(void* user, int frame_index, uint8_t* bgr, int width, int height, size_t step);
+    void (*convert)(void* user, int frame_index, uint8_t* bgr, int width, int height, size_t step);   /* may be NULL */
+    void* owned_transport;                                                                /* internal */
+} poppy_host_writer_io;
+int poppy_host_writer_create_io(poppy_host_writer** out, const poppy_host_writer_io* io, int width, int height, int ring_frames,
+                                int workers);
+void poppy_host_writer_destroy(poppy_host_writer* w);
+
+/* The C++ shim (poppy_b200/csrc/host/morph_images.hpp: poppy::Settings, poppy::morph_images, poppy::morph_sequence with
+ * the reference's argument order and semantics) behind C entry points, for callers and tests without a C++ toolchain:
+ * the shim keeps its own device context (per frame size / pyramid levels), runs the host stages and, for a sequence, the
+ * sliced chain render + writer ring; `write` receives the frames in order (reference src/poppy.hpp:177-243). */
+int poppy_shim_morph_images(int width, int height, int pyramid_levels, const uint8_t* corrected1, size_t step1,
+                            const uint8_t* corrected2, size_t step2, const float* gabor2, size_t gstep,
+                            const float* src_points1_xy, const float* src_points2_xy, int n, double shape_ratio,
+                            double mask_ratio, uint8_t* dst_bgr, size_t dst_step, float* morphed_xy);
+int poppy_shim_morph_sequence(int width, int height, int pyramid_levels, const uint8_t* corrected1, size_t step1,
+                              const uint8_t* corrected2, size_t step2, const float* gabor2, size_t gstep,
+                              const float* src_points1_xy, const float* src_points2_xy, int n, int number_of_frames,
+                              poppy_write_fn write, void* user);
+void poppy_shim_release(void);
+
 const char* poppy_host_last_error(void);
 
 #ifdef __cplusplus

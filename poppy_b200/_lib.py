@@ -46,6 +46,16 @@ def load():
         "poppy_morph_images": (i32, [vp, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, vp, vp, i32, C.c_double,
                                C.c_double, vp, C.c_size_t, vp]),
         "poppy_host_last_error": (C.c_char_p, []),
+        "poppy_shim_morph_images": (i32, [i32, i32, i32, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, vp, vp, i32, C.c_double, C.c_double,
+                                    vp, C.c_size_t, vp]),
+        "poppy_shim_morph_sequence": (i32, [i32, i32, i32, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, vp, vp, i32, i32, vp, vp]),
+        "poppy_shim_release": (None, []),
+        "poppy_host_writer_create": (i32, [C.POINTER(vp), vp, i32, vp, vp, i32, vp]),
+        "poppy_host_writer_create_io": (i32, [C.POINTER(vp), vp, i32, i32, i32, i32]),
+        "poppy_host_writer_submit": (i32, [vp, i32, i32, i32]),
+        "poppy_host_writer_flush": (i32, [vp]),
+        "poppy_host_writer_destroy": (None, [vp]),
+        "poppy_host_writer_destroy_cuda": (None, [vp]),
         "poppy_cuda_set_chunk_frames": (i32, [vp, i32]),
         "poppy_cuda_set_stage_timing": (i32, [vp, i32]),
         "poppy_cuda_set_unsharp_mode": (i32, [vp, i32]),
@@ -58,6 +68,10 @@ def load():
         "poppy_cuda_render": (i32, [vp, i32, vp, vp, vp, vp, i32]),
         "poppy_cuda_render_range": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
         "poppy_cuda_download": (i32, [vp, i32, i32, vp, C.c_size_t, C.c_size_t]),
+        "poppy_cuda_download_async": (i32, [vp, i32, i32, vp, C.c_size_t, C.c_size_t, u64p]),
+        "poppy_cuda_download_wait": (i32, [vp, C.c_uint64]),
+        "poppy_cuda_alloc_pinned": (i32, [C.c_size_t, C.POINTER(vp)]),
+        "poppy_cuda_free_pinned": (None, [vp]),
         "poppy_cuda_get_morphed_points": (i32, [vp, i32, vp]),
         "poppy_cuda_frame_device_ptr": (i32, [vp, i32, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "poppy_cuda_checksum": (i32, [vp, i32, i32, u64p]),
@@ -88,9 +102,12 @@ CUDA_ABI_SYMBOLS = [
     "poppy_cuda_launch_count", "poppy_cuda_stage_times", "poppy_cuda_debug_read", "poppy_cuda_last_error",
     "poppy_cuda_version", "poppy_cuda_get_info", "poppy_cuda_set_tile_list_capacity", "poppy_cuda_set_unsharp_mode",
     "poppy_cuda_unsharp_stats", "poppy_cuda_set_image", "poppy_cuda_set_source1_from_slot",
+    "poppy_cuda_download_async", "poppy_cuda_download_wait", "poppy_cuda_alloc_pinned", "poppy_cuda_free_pinned",
 ]
 HOST_ABI_SYMBOLS = [
     "poppy_host_morph_points", "poppy_host_triangulate", "poppy_host_chain_ratio", "poppy_host_plan_create",
     "poppy_host_plan_triangles", "poppy_host_plan_points", "poppy_host_plan_destroy", "poppy_morph_images",
-    "poppy_host_last_error",
+    "poppy_host_last_error", "poppy_host_writer_create", "poppy_host_writer_create_io", "poppy_host_writer_submit",
+    "poppy_host_writer_flush", "poppy_host_writer_destroy", "poppy_host_writer_destroy_cuda",
+    "poppy_shim_morph_images", "poppy_shim_morph_sequence", "poppy_shim_release",
 ]

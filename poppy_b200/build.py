@@ -23,6 +23,7 @@ HOST_SOURCES = [
     "host/delaunay.cpp",
     "host/morph_images.cpp",
     "host/host_abi.cpp",
+    "host/writer.cpp",
 ]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
@@ -82,7 +83,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         log.append("$ " + " ".join(cmd) + "\n" + out)
         if p.returncode != 0:
             raise RuntimeError("build failed:\n" + log[-1])
-    link = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart", "-lpthread"]
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart", "-lpthread"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log.append("$ " + " ".join(link) + "\n" + r.stdout)
     if r.returncode != 0:

@@ -76,7 +76,8 @@ void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const f
 // tile_flags (nullable): per frame and 128x32 tile, 0 = the tile is not needed (calm, see below)
 void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
                       size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
-                      float* out_fine, LevelDesc ol, int frames, const unsigned char* tile_flags, const CollapseMaps* maps);
+                      float* out_fine, LevelDesc ol, int frames, const unsigned char* tile_flags, const CollapseMaps* maps,
+                      int map_frame0 = 0);     // map_frame0: chunk frame index of the launch's first frame (the maps span the chunk)
 // level-0 collapse fused with convertTo(CV_8U, 255): stores cvRound(255 out[0]) into the frame ring (exactly the frame
 // wherever unsharp_mask() leaves the pixel untouched) and, per 4x8-pixel block and channel, whether out[0] left [0, 1] by
 // more than 0.001 there: ex[(f*3 + c) * ex_stride + by * ex_pitch + bx]

@@ -1209,7 +1209,7 @@ k_collapse_tma(const __grid_constant__ TmaMap tm_fine, const __grid_constant__ T
                size_t fstride, const float* __restrict__ g_coarse, const float* __restrict__ out_coarse, int cw, int ch, int cpitch,
                size_t cstride, float* __restrict__ out_fine, int opitch, size_t ostride, const unsigned char* __restrict__ tile_flags,
                const FrameParams* __restrict__ fp, uint8_t* __restrict__ frames_base, size_t frame_bytes, unsigned char* __restrict__ ex,
-               int ex_pitch, size_t ex_stride) {
+               int ex_pitch, size_t ex_stride, int map_frame0) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     const int f = blockIdx.z, warp = threadIdx.y, lane = threadIdx.x, c = warp < 3 ? warp : 0;
     if (tile_flags && !tile_flags[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
@@ -1244,7 +1244,7 @@ k_collapse_tma(const __grid_constant__ TmaMap tm_fine, const __grid_constant__ T
         __syncthreads();
         if (warp == 3) {
             if (lane == 0) {
-                const int fx0 = blockIdx.x * 128, a0 = fx0 >> 1;
+                const int fx0 = blockIdx.x * 128, a0 = fx0 >> 1, mf = map_frame0 + f;      // the maps span the whole chunk
 #pragma unroll 1
                 for (int k = 0; k < CL_R; ++k) {
                     const int s = k % CT_NS;
@@ -1256,14 +1256,14 @@ k_collapse_tma(const __grid_constant__ TmaMap tm_fine, const __grid_constant__ T
                     CtStage<L0>& S = stages[s];
                     if (L0) {
                         CtStage<true>& T = reinterpret_cast<CtStage<true>&>(S);
-                        tma_load_3d(T.fine, &tm_fine, fx0, 2 * (cy0 + k), 2 * f, bar);
-                        tma_load_3d(T.mask, &tm_mask, fx0, 2 * (cy0 + k), f, bar);
+                        tma_load_3d(T.fine, &tm_fine, fx0, 2 * (cy0 + k), 2 * mf, bar);
+                        tma_load_3d(T.mask, &tm_mask, fx0, 2 * (cy0 + k), mf, bar);
                     } else {
                         CtStage<false>& T = reinterpret_cast<CtStage<false>&>(S);
-                        tma_load_3d(T.fine, &tm_fine, fx0, 2 * (cy0 + k), 7 * f, bar);
+                        tma_load_3d(T.fine, &tm_fine, fx0, 2 * (cy0 + k), 7 * mf, bar);
                     }
-                    tma_load_3d(S.gc, &tm_gc, a0 - 4, cy0 + k + 1, 7 * f, bar);
-                    tma_load_3d(S.oc, &tm_oc, a0 - 4, cy0 + k + 1, 3 * f, bar);
+                    tma_load_3d(S.gc, &tm_gc, a0 - 4, cy0 + k + 1, 7 * mf, bar);
+                    tma_load_3d(S.oc, &tm_oc, a0 - 4, cy0 + k + 1, 3 * mf, bar);
                 }
             }
             return;
@@ -1327,7 +1327,7 @@ void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const f
         ensure_smem_attr(k_collapse_tma<false, false>, ct_smem<false, false>(), done);
         k_collapse_tma<false, false><<<grid, dim3(32, 4), ct_smem<false, false>(), st>>>(
             maps->fine, maps->mask, maps->gc, maps->oc, nullptr, 0, 0, nullptr, 0, 0, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse,
-            out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, out_fine, fl.pitch, fl.plane_stride, nullptr, nullptr, nullptr, 0, nullptr, 0, 0);
+            out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, out_fine, fl.pitch, fl.plane_stride, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, 0);
         return;
     }
     static SmemAttrOnce done;
@@ -1339,7 +1339,8 @@ void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const f
 
 void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
                       size_t m0stride, int w, int h, const float* g_coarse, const float* out_coarse, LevelDesc cl,
-                      float* out_fine, LevelDesc ol, int frames, const unsigned char* tile_flags, const CollapseMaps* maps) {
+                      float* out_fine, LevelDesc ol, int frames, const unsigned char* tile_flags, const CollapseMaps* maps,
+                      int map_frame0) {
     const dim3 grid(div_up(w, 128), div_up(h, 2 * CL_R), frames);
     if (maps && use_tma()) {
         static SmemAttrOnce done;
@@ -1347,7 +1348,7 @@ void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_
         k_collapse_tma<true, false><<<grid, dim3(32, 4), ct_smem<true, false>(), st>>>(
             maps->fine, maps->mask, maps->gc, maps->oc, warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse,
             out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, out_fine, ol.pitch, ol.plane_stride, tile_flags, nullptr, nullptr, 0, nullptr,
-            0, 0);
+            0, 0, map_frame0);
         return;
     }
     static SmemAttrOnce done;
@@ -1368,7 +1369,7 @@ void launch_collapse0_emit(cudaStream_t st, const uint32_t* warped, int wpitch, 
         ensure_smem_attr(k_collapse_tma<true, true>, ct_smem<true, true>(), done);
         k_collapse_tma<true, true><<<grid, dim3(32, 4), ct_smem<true, true>(), st>>>(
             maps->fine, maps->mask, maps->gc, maps->oc, warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse,
-            out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, nullptr, 0, 0, nullptr, fp, frames_base, frame_bytes, ex, ex_pitch, ex_stride);
+            out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, nullptr, 0, 0, nullptr, fp, frames_base, frame_bytes, ex, ex_pitch, ex_stride, 0);
         return;
     }
     static SmemAttrOnce done;

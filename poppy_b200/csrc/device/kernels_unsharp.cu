@@ -74,6 +74,17 @@ __device__ __forceinline__ float row9(const float* t, bool fused) {
     return s;
 }
 
+// the fused symmetric column filter on two adjacent columns at once (sm_100 FADD2 / FFMA2: both halves individually rounded,
+// so the results are those of col9(..., true) per column)
+__device__ __forceinline__ float2 col9_fused2(float2 w0, float2 w1, float2 w2, float2 w3, float2 w4, float2 w5, float2 w6, float2 w7,
+                                              float2 w8) {
+    float2 s = __ffma2_rn(make_float2(gk(0), gk(0)), w4, make_float2(0.f, 0.f));
+    s = __ffma2_rn(make_float2(gk(1), gk(1)), __fadd2_rn(w5, w3), s);
+    s = __ffma2_rn(make_float2(gk(2), gk(2)), __fadd2_rn(w6, w2), s);
+    s = __ffma2_rn(make_float2(gk(3), gk(3)), __fadd2_rn(w7, w1), s);
+    return __ffma2_rn(make_float2(gk(4), gk(4)), __fadd2_rn(w8, w0), s);
+}
+
 // symmetric column filter — w[0..8] top to bottom
 __device__ __forceinline__ float col9(float w0, float w1, float w2, float w3, float w4, float w5, float w6, float w7,
                                       float w8, bool fused) {
@@ -197,10 +208,13 @@ __device__ __forceinline__ void us_col_pass(const UsThread& T, const float* rp_t
             if (!INTERIOR && T.h == 1) {
                 b = win[4 + i];
             } else if (fused) {
-                b.x = col9(win[i].x, win[i + 1].x, win[i + 2].x, win[i + 3].x, win[i + 4].x, win[i + 5].x, win[i + 6].x, win[i + 7].x, win[i + 8].x, true);
-                b.y = col9(win[i].y, win[i + 1].y, win[i + 2].y, win[i + 3].y, win[i + 4].y, win[i + 5].y, win[i + 6].y, win[i + 7].y, win[i + 8].y, true);
-                b.z = col9(win[i].z, win[i + 1].z, win[i + 2].z, win[i + 3].z, win[i + 4].z, win[i + 5].z, win[i + 6].z, win[i + 7].z, win[i + 8].z, true);
-                b.w = col9(win[i].w, win[i + 1].w, win[i + 2].w, win[i + 3].w, win[i + 4].w, win[i + 5].w, win[i + 6].w, win[i + 7].w, win[i + 8].w, true);
+#define POPPY_LO(k) make_float2(win[i + (k)].x, win[i + (k)].y)
+#define POPPY_HI(k) make_float2(win[i + (k)].z, win[i + (k)].w)
+                const float2 lo = col9_fused2(POPPY_LO(0), POPPY_LO(1), POPPY_LO(2), POPPY_LO(3), POPPY_LO(4), POPPY_LO(5), POPPY_LO(6), POPPY_LO(7), POPPY_LO(8));
+                const float2 hi = col9_fused2(POPPY_HI(0), POPPY_HI(1), POPPY_HI(2), POPPY_HI(3), POPPY_HI(4), POPPY_HI(5), POPPY_HI(6), POPPY_HI(7), POPPY_HI(8));
+#undef POPPY_LO
+#undef POPPY_HI
+                b = make_float4(lo.x, lo.y, hi.x, hi.y);
             } else {
                 b.x = col9(win[i].x, win[i + 1].x, win[i + 2].x, win[i + 3].x, win[i + 4].x, win[i + 5].x, win[i + 6].x, win[i + 7].x, win[i + 8].x, 3 * (T.gx0 + 0) + c < T.tail_from);
                 b.y = col9(win[i].y, win[i + 1].y, win[i + 2].y, win[i + 3].y, win[i + 4].y, win[i + 5].y, win[i + 6].y, win[i + 7].y, win[i + 8].y, 3 * (T.gx0 + 1) + c < T.tail_from);
@@ -208,7 +222,11 @@ __device__ __forceinline__ void us_col_pass(const UsThread& T, const float* rp_t
                 b.w = col9(win[i].w, win[i + 1].w, win[i + 2].w, win[i + 3].w, win[i + 4].w, win[i + 5].w, win[i + 6].w, win[i + 7].w, win[i + 8].w, 3 * (T.gx0 + 3) + c < T.tail_from);
             }
             const float4 x = *reinterpret_cast<const float4*>(xs_t + slot * US_XROW);
-            d = make_float4(__fsub_rn(x.x, b.x), __fsub_rn(x.y, b.y), __fsub_rn(x.z, b.z), __fsub_rn(x.w, b.w));
+            {   // x - b, two columns per instruction: fma(b, -1, x) rounds the exact difference once
+                const float2 dlo = __ffma2_rn(make_float2(b.x, b.y), make_float2(-1.f, -1.f), make_float2(x.x, x.y));
+                const float2 dhi = __ffma2_rn(make_float2(b.z, b.w), make_float2(-1.f, -1.f), make_float2(x.z, x.w));
+                d = make_float4(dlo.x, dlo.y, dhi.x, dhi.y);
+            }
             // columns past the image hold padding: keep them out of the flags
             const float m0 = fabsf(d.x), m1 = (INTERIOR || T.gx0 + 1 < T.w) ? fabsf(d.y) : 0.f,
                         m2 = (INTERIOR || T.gx0 + 2 < T.w) ? fabsf(d.z) : 0.f, m3 = (INTERIOR || T.gx0 + 3 < T.w) ? fabsf(d.w) : 0.f;

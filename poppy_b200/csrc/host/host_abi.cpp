@@ -50,6 +50,20 @@ struct poppy_host_plan {
     std::vector<int32_t> offsets;                // frames + 1
 };
 
+// ---- the C++ shim (poppy::morph_images / poppy::morph_sequence, morph_images.hpp) behind C entry points ------------------
+namespace {
+template <class F> int shim_guard(F&& f) {
+    try { f(); return 0; }
+    catch (const poppy::MorphError& e) { return host_fail(POPPY_CUDA_ERR_INVALID, e.what()); }
+    catch (const std::exception& e) { return host_fail(POPPY_CUDA_ERR_INVALID, e.what()); }
+}
+poppy::Image8 view8(const uint8_t* p, int w, int h, size_t step) {
+    poppy::Image8 v;
+    v.data = const_cast<uint8_t*>(p); v.cols = w; v.rows = h; v.step = step;
+    return v;
+}
+}  // namespace
+
 extern "C" {
 
 const char* poppy_host_last_error(void) { return g_host_error.c_str(); }
@@ -200,5 +214,36 @@ int poppy_morph_images(poppy_cuda_ctx* ctx, const uint8_t* c1, size_t step1, con
         return host_fail(rc, poppy_cuda_last_error(ctx));
     return 0;
 }
+
+int poppy_shim_morph_images(int w, int h, int pyramid_levels, const uint8_t* c1, size_t step1, const uint8_t* c2, size_t step2,
+                            const float* gabor2, size_t gstep, const float* sp1, const float* sp2, int n, double shape_ratio,
+                            double mask_ratio, uint8_t* dst, size_t dst_step, float* morphed_xy) {
+    if (!c1 || !c2 || !gabor2 || !dst || n < 0 || (n > 0 && (!sp1 || !sp2))) return host_fail(POPPY_CUDA_ERR_INVALID, "null argument");
+    return shim_guard([&] {
+        poppy::Settings::instance().pyramid_levels = (size_t)pyramid_levels;
+        poppy::Image8 img1 = view8(c1, w, h, step1), img2 = view8(c2, w, h, step2), none, out = view8(dst, w, h, dst_step);
+        poppy::Image32F g;
+        g.data = gabor2; g.cols = w; g.rows = h; g.step = gstep;
+        std::vector<Point2f> a = to_points(sp1, n), b = to_points(sp2, n), m;
+        poppy::morph_images(img1, img2, img1, img2, g, none, none, out, none, m, a, b, shape_ratio, mask_ratio, 0.0);
+        if (morphed_xy && n) std::memcpy(morphed_xy, m.data(), (size_t)n * sizeof(Point2f));
+    });
+}
+
+int poppy_shim_morph_sequence(int w, int h, int pyramid_levels, const uint8_t* c1, size_t step1, const uint8_t* c2, size_t step2,
+                              const float* gabor2, size_t gstep, const float* sp1, const float* sp2, int n, int n_frames,
+                              poppy_write_fn write, void* user) {
+    if (!c1 || !c2 || !gabor2 || !write || n < 0 || (n > 0 && (!sp1 || !sp2))) return host_fail(POPPY_CUDA_ERR_INVALID, "null argument");
+    return shim_guard([&] {
+        poppy::Settings::instance().pyramid_levels = (size_t)pyramid_levels;
+        poppy::Image32F g;
+        g.data = gabor2; g.cols = w; g.rows = h; g.step = gstep;
+        int index = 0;
+        poppy::morph_sequence(view8(c1, w, h, step1), view8(c2, w, h, step2), g, to_points(sp1, n), to_points(sp2, n), n_frames,
+                              [&](const poppy::Image8& f) { write(user, index++, f.data, f.cols, f.rows, f.step); });
+    });
+}
+
+void poppy_shim_release(void) { poppy::release_cached_contexts(); }
 
 }  // extern "C"

@@ -44,6 +44,9 @@ poppy_cuda_ctx* context_for(int w, int h, int levels, int n_points, int n_tri, i
         g_cached.reset();
         throw MorphError(msg);
     }
+    // both entry points render one frame per kernel batch (a single frame, or a chain = a recurrence): size the scratch for
+    // that instead of the 32-frame batches of direct-mode sequences
+    poppy_cuda_set_chunk_frames(k->ctx, 1);
     return k->ctx;
 }
 
@@ -118,14 +121,28 @@ void morph_sequence(const Image8& corrected1, const Image8& corrected2, const Im
     poppy_cuda_ctx* c = context_for(w, h, (int)Settings::instance().pyramid_levels, n, max_tri, N);
     cu(c, poppy_cuda_set_pair(c, corrected1.data, corrected1.step, corrected2.data, corrected2.step, gabor2.data, gabor2.step));
     cu(c, poppy_cuda_set_points(c, p1, p2, n));
-    cu(c, poppy_cuda_render(c, N, ratio.data(), mask.data(), tri, offs, 1));
-    Image8 frame;
-    frame.create(w, h);
-    for (int j = 0; j < N; ++j) {
-        cu(c, poppy_cuda_download(c, j, 1, frame.data, frame.step, frame.step * h));
-        cu(c, poppy_cuda_sync(c));
-        write(frame);
+    // The chain is rendered slice by slice (frame j-1 stays in HBM as frame j's source across the calls) and every finished
+    // slice is handed to the writer ring: slice k+1 renders while slice k downloads and slice k-1 is being written.
+    struct Sink { const std::function<void(const Image8&)>* write; } sink{&write};
+    auto deliver = [](void* u, int, uint8_t* bgr, int fw, int fh, size_t step) {
+        Image8 f;
+        f.data = bgr; f.cols = fw; f.rows = fh; f.step = step;
+        (*static_cast<Sink*>(u)->write)(f);
+    };
+    poppy_host_writer* wr = nullptr;
+    if (poppy_host_writer_create(&wr, c, std::min(N, 8), deliver, nullptr, 0, &sink) != 0)
+        throw MorphError("morph_sequence: cannot create the writer ring");
+    struct WriterGuard { poppy_host_writer* w; ~WriterGuard() { poppy_host_writer_destroy_cuda(w); } } wguard{wr};
+    const int S = 4;
+    std::vector<int32_t> so;
+    for (int a = 0; a < N; a += S) {
+        const int cnt = std::min(S, N - a);
+        so.assign(cnt + 1, 0);
+        for (int i = 0; i <= cnt; ++i) so[i] = offs[a + i] - offs[a];
+        cu(c, poppy_cuda_render_range(c, a, cnt, ratio.data() + a, mask.data() + a, tri + (size_t)offs[a] * 3, so.data(), 1));
+        if (poppy_host_writer_submit(wr, a, cnt, a) != 0) throw MorphError(std::string("morph_sequence: ") + poppy_cuda_last_error(c));
     }
+    if (poppy_host_writer_flush(wr) != 0) throw MorphError("morph_sequence: a frame download failed");
 }
 
 }  // namespace poppy

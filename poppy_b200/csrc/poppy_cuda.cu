@@ -51,6 +51,9 @@ struct poppy_cuda_ctx {
     uint8_t* d_stage_u8 = nullptr;       // upload staging of set_image, kept between calls
     float* d_stage_f32 = nullptr;
     int n_points = 0, last_frames = 0;
+    int chain_next_slot = -1;            // ring slot at which a sliced chain render may continue (-1: no chain in progress)
+    std::vector<cudaEvent_t> tickets;    // download tickets (poppy_cuda_download_async), indexed ticket % size
+    uint64_t next_ticket = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // downloads run on their own stream so that they overlap the render of other ring slots; a render that would
@@ -108,6 +111,8 @@ struct poppy_cuda_ctx {
     // every pixel. 0 = adaptive (the calm route while the share of flagged chunks seen on recent frames stays low, the dense
     // route otherwise, probing the calm route now and then); 1 = dense always (forced by keep_stages); 2 = calm always.
     int unsharp_mode = 0;
+    int l0_group = 0;                        // POPPY_CUDA_L0_GROUP: frames per (level-0 collapse, unsharp) launch pair of the dense route
+    int l0_chunk_rows = 0;                   // POPPY_CUDA_US_ROWS: rows per CTA of the dense unsharp pass (0: 216)
     double calm_share = 0.0;                 // running share of flagged strip chunks on the calm route
     unsigned route_tick = 0;
     int mm_pitch = 0;                        // blocks per row of the clamp-excess table, padded
@@ -364,8 +369,10 @@ int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* s
     if (tri_total) CU_TRY(c, cudaMemcpyAsync(ln.d_tri, ht, (size_t)tri_total * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CU_TRY(c, cudaEventRecord(ln.ev_staged, st));
 
-    const bool chained = chain && first > 0;
-    const float2* p1 = chained ? c->d_morphed + (size_t)(first - 1) * c->max_points : c->d_pts1;
+    // a chain continues from the frame before it: the previous frame of this call, or - when a chain is rendered slice by
+    // slice - the last frame of the previous call (ring slot slot0 + first - 1, whose pixels are still in t_src[2])
+    const bool chained = chain && (slot0 + first) > 0;
+    const float2* p1 = chained ? c->d_morphed + (size_t)(slot0 + first - 1) * c->max_points : c->d_pts1;
     const cudaTextureObject_t src1 = chained ? c->t_src[2] : c->t_src[0];
     float2* morphed = c->d_morphed + (size_t)(slot0 + first) * c->max_points;
     const int n = c->n_points, w = c->w, h = c->h, L = c->levels;
@@ -438,12 +445,21 @@ int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* s
                                  ln.d_chunk_flags);
         }
     } else {
-        {   Scope s(c, KC_COLLAPSE, st);
-            launch_collapse0(st, ln.d_warped, c->pitch0(), c->padded_pixels(), ln.d_mask0, c->pitch0(), c->padded_pixels(), w, h,
-                             g_level(c, ln, 1), o_level(c, ln, 1), c->lv[1], o_level(c, ln, 0), c->lv[0], nb, nullptr, level_maps(ln, 0));
-        }
-        {   Scope s(c, KC_UNSHARP, st);
-            launch_unsharp_store(st, o_level(c, ln, 0), c->lv[0], ln.d_fp, c->d_frames, c->frame_bytes(), nb, 0, nullptr);
+        // Dense route in groups of `l0_group` frames: the level-0 collapse of a group writes lapBlend into one small scratch
+        // that the unsharp kernel reads right away and the next group overwrites, so the 12 B/px planes live in the 126 MB L2
+        // instead of crossing HBM twice (0: one launch pair for the whole chunk).
+        const int G = (c->l0_group > 0 && c->l0_group < nb) ? c->l0_group : nb;
+        const size_t pp = c->padded_pixels();
+        for (int f0 = 0; f0 < nb; f0 += G) {
+            const int n = std::min(G, nb - f0);
+            {   Scope s(c, KC_COLLAPSE, st);
+                launch_collapse0(st, ln.d_warped + (size_t)f0 * 2 * pp, c->pitch0(), pp, ln.d_mask0 + (size_t)f0 * pp, c->pitch0(), pp, w, h,
+                                 g_level(c, ln, 1) + (size_t)f0 * 7 * c->lv[1].plane_stride, o_level(c, ln, 1) + (size_t)f0 * 3 * c->lv[1].plane_stride,
+                                 c->lv[1], o_level(c, ln, 0), c->lv[0], n, nullptr, level_maps(ln, 0), f0);
+            }
+            {   Scope s(c, KC_UNSHARP, st);
+                launch_unsharp_store(st, o_level(c, ln, 0), c->lv[0], ln.d_fp + f0, c->d_frames, c->frame_bytes(), n, c->l0_chunk_rows, nullptr);
+            }
         }
         c->dense_chunks_total += (uint64_t)nb * chunks_per_frame;
         if (c->unsharp_mode == 0 && !c->keep_stages && (++c->route_tick % kCalmProbeEvery) == 0 && !ln.calm_pending) {
@@ -461,7 +477,7 @@ int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* s
     }
     if (chain) {
         Scope s(c, KC_MISC, st);
-        launch_bgr_to_bgrx(st, c->d_frames + (size_t)(first + nb - 1) * c->frame_bytes(), c->d_src_stage, w, h);
+        launch_bgr_to_bgrx(st, c->d_frames + (size_t)(slot0 + first + nb - 1) * c->frame_bytes(), c->d_src_stage, w, h);
         CU_TRY(c, cudaMemcpy2DToArrayAsync(c->a_src[2], 0, 0, c->d_src_stage, (size_t)w * 4, (size_t)w * 4, h,
                                            cudaMemcpyDeviceToDevice, st));
     }
@@ -500,6 +516,8 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
     c->max_points = max_points; c->max_tri = max_triangles; c->max_frames = max_batch_frames;
     if (const char* e = std::getenv("POPPY_CUDA_SINGLE_LANE")) c->single_lane = e[0] == '1';   // A/B switch for profiling
     if (const char* e = std::getenv("POPPY_CUDA_LANES")) c->want_lanes = std::max(1, std::min(4, std::atoi(e)));
+    if (const char* e = std::getenv("POPPY_CUDA_L0_GROUP")) c->l0_group = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("POPPY_CUDA_US_ROWS")) c->l0_chunk_rows = std::max(0, std::atoi(e)) / 8 * 8;
     auto bail = [&](int rc) { g_create_error = c->err; poppy_cuda_destroy(c); return rc; };
 #define CR_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
         fail(c, POPPY_CUDA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(POPPY_CUDA_ERR_CUDA); } } while (0)
@@ -580,6 +598,7 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
     for (auto& l : c->lane) if (l.stream) cudaStreamSynchronize(l.stream);
     collect_timing(c);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->tickets) if (e) cudaEventDestroy(e);
     free_chunk(c);
     cudaFree(c->d_src_stage); cudaFree(c->d_mbasis); cudaFree(c->d_stage_u8); cudaFree(c->d_stage_f32);
     for (int i = 0; i < 3; ++i) {
@@ -751,7 +770,9 @@ int poppy_cuda_render(poppy_cuda_ctx* c, int n_frames, const float* shape, const
 int poppy_cuda_render_range(poppy_cuda_ctx* c, int first_slot, int n_frames, const float* shape, const double* mask,
                             const int32_t* tri_idx, const int32_t* tri_off, int chain) {
     if (!c) return POPPY_CUDA_ERR_INVALID;
-    if (first_slot < 0 || (chain && first_slot != 0)) return fail(c, POPPY_CUDA_ERR_INVALID, "bad first_slot %d (a chain starts at slot 0)", first_slot);
+    if (first_slot < 0) return fail(c, POPPY_CUDA_ERR_INVALID, "bad first_slot %d", first_slot);
+    if (chain && first_slot > 0 && c->chain_next_slot != first_slot)
+        return fail(c, POPPY_CUDA_ERR_STATE, "a chain continues at the slot after its last rendered frame (%d), not at %d", c->chain_next_slot, first_slot);
     if (!c->have_pair || !c->have_points) return fail(c, POPPY_CUDA_ERR_STATE, "set_pair and set_points must precede render");
     if (!shape || !mask || !tri_off) return fail(c, POPPY_CUDA_ERR_INVALID, "null argument");
     if (!tri_idx && n_frames >= 1 && tri_off[n_frames] != tri_off[0]) return fail(c, POPPY_CUDA_ERR_INVALID, "null triangle list");
@@ -798,6 +819,7 @@ int poppy_cuda_render_range(poppy_cuda_ctx* c, int first_slot, int n_frames, con
     }
     CU_TRY(c, cudaEventRecord(c->ev_end, c->stream));
     c->last_frames = first_slot + n_frames;
+    c->chain_next_slot = chain ? first_slot + n_frames : -1;
     return 0;
 }
 
@@ -824,6 +846,38 @@ int poppy_cuda_download(poppy_cuda_ctx* c, int first, int count, uint8_t* dst, s
     else { c->copy_lo = std::min(c->copy_lo, first); c->copy_hi = std::max(c->copy_hi, first + count); }
     return 0;
 }
+
+int poppy_cuda_download_async(poppy_cuda_ctx* c, int first, int count, uint8_t* dst, size_t step, size_t frame_stride,
+                              uint64_t* ticket) {
+    if (!c || !ticket) return POPPY_CUDA_ERR_INVALID;
+    if (int rc = poppy_cuda_download(c, first, count, dst, step, frame_stride)) return rc;
+    if (c->tickets.empty()) {
+        c->tickets.resize(64, nullptr);
+        for (auto& e : c->tickets) CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const uint64_t t = c->next_ticket++;
+    CU_TRY(c, cudaEventRecord(c->tickets[t % c->tickets.size()], c->copy_stream));
+    *ticket = t;
+    return 0;
+}
+
+int poppy_cuda_download_wait(poppy_cuda_ctx* c, uint64_t ticket) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (ticket >= c->next_ticket) return POPPY_CUDA_ERR_INVALID;
+    // a ticket older than the pool is long complete: the copy stream is in order and its event slot has been re-recorded
+    // by a later download, which can only finish after this one
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaEventSynchronize(c->tickets[ticket % c->tickets.size()]) != cudaSuccess)
+        return POPPY_CUDA_ERR_CUDA;
+    return 0;
+}
+
+int poppy_cuda_alloc_pinned(size_t bytes, void** out) {
+    if (!out) return POPPY_CUDA_ERR_INVALID;
+    *out = nullptr;
+    return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? 0 : POPPY_CUDA_ERR_CUDA;
+}
+
+void poppy_cuda_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
 int poppy_cuda_get_morphed_points(poppy_cuda_ctx* c, int frame, float* xy) {
     if (!c) return POPPY_CUDA_ERR_INVALID;
@@ -930,7 +984,8 @@ int poppy_cuda_debug_read(poppy_cuda_ctx* c, int stage, int frame, void* dst, si
         std::vector<TriInverse> tmp(std::max(P.n_tri, 1));
         CU_TRY(c, cudaMemcpy(tmp.data(), c->lane[0].d_inv, (size_t)P.n_tri * sizeof(TriInverse), cudaMemcpyDeviceToHost));
         float* o = (float*)dst;
-        for (int i = 0; i < P.n_tri; ++i) std::memcpy(o + 9 * i, stage == POPPY_STAGE_INV_M1 ? tmp[i].a : tmp[i].b, 36);
+        for (int i = 0; i < P.n_tri; ++i)
+            for (int j = 0; j < 9; ++j) o[9 * i + j] = stage == POPPY_STAGE_INV_M1 ? tmp[i].m[j].x : tmp[i].m[j].y;
         return 0;
     }
     case POPPY_STAGE_WARPED1:

@@ -28,12 +28,24 @@ def test_dominant_kernel_roofline_fields():
     d = b.dominant_kernel_roofline(kern, 3840, 2160, 600, 32, 6532.2, traffic, 6)
     assert d["kernel"] == "blend_collapse" and d["unit"] == "GB/s"
     assert 0 < d["frac"] < 1 and abs(d["achieved"] / d["peak"] - d["frac"]) < 1e-12
-    # 7 launches of a 32-frame chunk rated together; traffic scaled to the same frames
-    frames = 600 * 7 / 133
-    assert abs(d["traffic"] - 4.2e8 * frames) < 1e3
-    assert d["algorithmic_bytes_per_launch"] > 0.9 * d["traffic"] * 0.9
+    # the 7 launches of a 32-frame chunk are rated together; traffic and algorithmic bytes cover the same 32 frames
+    assert d["launches_per_chunk"] == 7 and abs(d["us_per_launch"] - 7 * 430.0) < 1e-9
+    assert abs(d["traffic"] - 4.2e8 * 32) < 1e3
+    assert d["algorithmic_bytes_per_launch"] > 0.8 * d["traffic"]
     d2 = b.dominant_kernel_roofline(kern[1:], 3840, 2160, 600, 32, 6532.2, traffic, 6)
-    assert d2["kernel"] == "raster_warp" and d2["algorithmic_bytes_per_launch"] == int((8 * 3840 * 2160 + 8 * 3840 * 2160 / 32) * 600 / 19)
+    assert d2["kernel"] == "raster_warp" and d2["algorithmic_bytes_per_launch"] == int((8 * 3840 * 2160 + 8 * 3840 * 2160 / 32) * 32)
+    # achieved = the class's algorithmic bytes of the step / its device time
+    assert abs(d2["achieved"] - (8 * 3840 * 2160 + 8 * 3840 * 2160 / 32) * 600 / 50.2e-3 / 1e9) < 1e-6
+
+
+def test_job_configs_are_identical_for_both_arms():
+    """The reference arm and the CUDA arm print the same `config` object (the driver compares them)."""
+    import argparse
+    b = _bench()
+    a = argparse.Namespace(mode="chain", workload="4k", total_frames=0, frames=0, ring=0)
+    j0, j1 = b.Job(a, 0, 1), b.Job(a, 0, 1)
+    assert j0.config() == j1.config() and j0.F == 60 and j0.L == 64 and (j0.W, j0.H) == (512, 512)
+    assert j0.phases[0] == 0 and abs(j0.masks[-1] - 1.0) < 1e-12
 
 
 def test_committed_traffic_file_is_well_formed():

@@ -220,3 +220,87 @@ def test_render_range_streams_slices_through_the_ring(native_lib):
         assert bits_differ(r.download(0, 5), want[5:10]) == 0
         with pytest.raises(Exception):
             r.render(phases[:5], masks[:5], plan.tri_idx[:plan.tri_offsets[5]], plan.tri_offsets[:6], first_slot=F - 2)
+
+
+# ---- the C++ shim (poppy::morph_images / poppy::morph_sequence) through its C entry points --------------------------
+_WRITE = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_size_t)
+
+
+def test_cpp_shim_morph_images_matches_reference(native_lib):
+    ref = _ref()
+    w, h, levels = 230, 170, 7
+    inp = synth.block_inputs(w, h, 50, seed=61)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    dst = np.zeros((h, w, 3), np.uint8)
+    mp = np.zeros((len(inp.pts1), 2), np.float32)
+    try:
+        rc = native_lib.poppy_shim_morph_images(w, h, levels, p(inp.bgr1), w * 3, p(inp.bgr2), w * 3, p(inp.gabor2), w * 12, p(inp.pts1),
+                                                p(inp.pts2), len(inp.pts1), 0.3, 0.7, p(dst), w * 3, p(mp))
+        assert rc == 0, native_lib.poppy_host_last_error()
+    finally:
+        native_lib.poppy_shim_release()
+    want, want_pts = ref.morph_images(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, 0.3, 0.7, levels)
+    assert bits_differ(dst, want) == 0 and bits_differ(mp, want_pts) == 0
+
+
+def test_cpp_shim_morph_sequence_writes_the_golden_chain_in_order(native_lib):
+    """poppy::morph_sequence: the chain rendered slice by slice (frame j-1 resident across the calls) with every slice handed
+    to the writer ring; the frames reach `write` in order and equal the reference frame loop's."""
+    g = np.load(os.path.join(GOLDEN, "chain_shapes_80x64_N12_L64.npz"))
+    bgr1, bgr2, gab = (np.ascontiguousarray(g[k]) for k in ("bgr1", "bgr2", "gabor2"))
+    pts1, pts2 = np.ascontiguousarray(g["pts1"], np.float32), np.ascontiguousarray(g["pts2"], np.float32)
+    h, w = bgr1.shape[:2]
+    N = int(g["n_frames"])
+    got = []
+
+    def write(user, idx, bgr, fw, fh, step):
+        got.append((idx, np.ctypeslib.as_array(bgr, shape=(fh * step,)).reshape(fh, step)[:, :fw * 3].reshape(fh, fw, 3).copy()))
+
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    cb = _WRITE(write)
+    try:
+        rc = native_lib.poppy_shim_morph_sequence(w, h, int(g["levels"]), p(bgr1), w * 3, p(bgr2), w * 3, p(gab), w * 12, p(pts1), p(pts2),
+                                                  len(pts1), N, cb, None)
+        assert rc == 0, native_lib.poppy_host_last_error()
+    finally:
+        native_lib.poppy_shim_release()
+    assert [i for i, _ in got] == list(range(N))
+    for j, (_, f) in enumerate(got):
+        assert bits_differ(f, g["frames"][j]) == 0, f"chain frame {j}"
+
+
+@pytest.mark.parametrize("n", [2, 0])
+def test_fewer_than_three_points_render_like_the_reference(n):
+    """No triangle can be formed: the reference blends the unwarped pair (an empty Delaunay mesh); so does the renderer."""
+    ref = _ref()
+    w, h, levels = 96, 72, 5
+    inp = synth.make_inputs(w, h, 10, 4.0, seed=71)
+    p1, p2 = inp.pts1[:n].copy(), inp.pts2[:n].copy()
+    api.Settings.instance().pyramid_levels = levels
+    dst, mp = api.morph_images(inp.bgr1, inp.bgr2, inp.bgr1, inp.bgr2, inp.gabor2, p1, p2, 0.4, 0.4)
+    want, want_pts = ref.morph_images(inp.bgr1, inp.bgr2, inp.gabor2, p1, p2, 0.4, 0.4, levels)
+    assert bits_differ(dst, want) == 0 and mp.shape == want_pts.shape and (n == 0 or bits_differ(mp, want_pts) == 0)
+
+
+def test_sliced_chain_continues_across_render_calls(native_lib):
+    """A chain rendered in slices (chain = 1, first_slot > 0 continues the previous call) equals the one-call chain."""
+    from poppy_b200.renderer import MorphRenderer
+    g = np.load(os.path.join(GOLDEN, "chain_shapes_80x64_N12_L64.npz"))
+    h, w = g["bgr1"].shape[:2]
+    N = int(g["n_frames"])
+    ratio = np.array([host.chain_ratio(j, N) for j in range(N)], np.float64)
+    plan = host.SequencePlan(g["pts1"], g["pts2"], w, h, ratio.astype(np.float32), chain=True)
+    offs = plan.tri_offsets
+    with MorphRenderer(w, h, int(g["levels"]), len(g["pts1"]), plan.max_triangles, N) as r:
+        r.set_pair(np.ascontiguousarray(g["bgr1"]), np.ascontiguousarray(g["bgr2"]), np.ascontiguousarray(g["gabor2"]))
+        r.set_points(g["pts1"], g["pts2"])
+        for a in range(0, N, 5):
+            b = min(a + 5, N)
+            r.render(ratio[a:b].astype(np.float32), ratio[a:b], plan.tri_idx[offs[a]:offs[b]], offs[a:b + 1] - offs[a], chain=True,
+                     first_slot=a)
+        frames = r.download(0, N)
+        with pytest.raises(Exception):          # a chain cannot continue anywhere but after its last frame
+            r.render(ratio[:2].astype(np.float32), ratio[:2], plan.tri_idx[offs[0]:offs[2]], offs[0:3] - offs[0], chain=True, first_slot=3)
+    plan.close()
+    for j in range(N):
+        assert bits_differ(frames[j], g["frames"][j]) == 0, f"chain frame {j}"
