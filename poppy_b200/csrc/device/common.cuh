@@ -35,14 +35,15 @@ struct __align__(16) TriRaster {
 };
 static_assert(sizeof(TriRaster) == 64, "TriRaster layout");
 
-// The two inverse matrices create_map() applies per pixel (reference src/algo.cpp:154-175), element-interleaved:
-// m[i] = (inv(M1)[i], inv(M2)[i]), so that the sampler evaluates both maps with packed fp32 instructions (one FFMA2 / FADD2
-// = the operation for image 1 and for image 2). 80 bytes: five aligned 16-byte loads.
+// The two inverse matrices create_map() applies per pixel (reference src/algo.cpp:154-175). 96 bytes: each matrix is
+// three aligned 16-byte loads for the warps that sample its image.
 struct __align__(16) TriInverse {
-    float2 m[9];
-    float2 pad;
+    float a[9];         // inv(M1): maps a morphed-frame pixel into image 1
+    float pad_a[3];
+    float b[9];         // inv(M2): maps it into image 2
+    float pad_b[3];
 };
-static_assert(sizeof(TriInverse) == 80, "TriInverse layout");
+static_assert(sizeof(TriInverse) == 96, "TriInverse layout");
 
 // One pyramid level of a frame chunk. Planes are row-major with `pitch` floats per row; plane p of frame f
 // starts at base + ((size_t)f * planes + p) * plane_stride.

@@ -192,13 +192,10 @@ __global__ void k_tri_geometry(const int3* __restrict__ tri_idx, const FramePara
         M1[i] = fmaf(H[i], r, __fmul_rn(eye, omr));      // eye*(1-r) + H*r    via scaleAdd_32f (algo.cpp:130)
         M2[i] = fmaf(iH[i], omr, __fmul_rn(eye, r));     // eye*r + inv(H)*(1-r)               (algo.cpp:131)
     }
-    float ia[9], ib[9];
-    inv3(M1, ia);
-    inv3(M2, ib);
     TriInverse out;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) out.m[i] = make_float2(ia[i], ib[i]);
-    out.pad = make_float2(0.f, 0.f);
+    inv3(M1, out.a);
+    inv3(M2, out.b);
+    out.pad_a[0] = out.pad_a[1] = out.pad_a[2] = out.pad_b[0] = out.pad_b[1] = out.pad_b[2] = 0.f;
     inv_out[(size_t)f * max_tri + t] = out;
 }
 

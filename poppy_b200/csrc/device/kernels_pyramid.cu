@@ -30,6 +30,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "pixel_ops.cuh"
+#include "tma.cuh"
 
 namespace poppy {
 
@@ -155,7 +156,7 @@ __device__ __forceinline__ float2 down_rowpass(const float* __restrict__ plane, 
 
 // One chunk (64 output columns) x DN_R output rows of one plane. Flags: bit 0/1 = vector-body association of the row
 // pass at xo / xo+1, bit 2/3 = of the column pass.
-template <bool INTERIOR>
+template <bool INTERIOR, int R = DN_R>
 __device__ __forceinline__ void down_chunk_f32(const float* __restrict__ sp, int sw, int sh, int spitch, float* __restrict__ dp,
                                                int dw, int dh, int dpitch, int xo, int y0, int lane, unsigned flags) {
     const bool ha = flags & 1u, hb = flags & 2u, va = flags & 4u, vb = flags & 8u, has_b = INTERIOR || xo + 1 < dw;
@@ -171,12 +172,12 @@ __device__ __forceinline__ void down_chunk_f32(const float* __restrict__ sp, int
     down_load<INTERIOR>(sp, spitch, sh, 2 * y0 + 1, xo, lane, ra);
     down_load<INTERIOR>(sp, spitch, sh, 2 * y0 + 2, xo, lane, rb);
 #pragma unroll 1
-    for (int k = 0; k < DN_R; ++k) {
+    for (int k = 0; k < R; ++k) {
         const int y = y0 + k;
         if (!INTERIOR && y >= dh) break;
         h3 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y + 1, xo, lane, ra, ha, hb, has_b);
         h4 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y + 2, xo, lane, rb, ha, hb, has_b);
-        if (k + 1 < DN_R) {
+        if (k + 1 < R) {
             down_load<INTERIOR>(sp, spitch, sh, 2 * y + 3, xo, lane, ra);
             down_load<INTERIOR>(sp, spitch, sh, 2 * y + 4, xo, lane, rb);
         }
@@ -202,26 +203,29 @@ __device__ __forceinline__ bool down_pair_interior(int xo, int sw, int dw, unsig
 
 }  // namespace
 
-// block (32, 4); grid (ceil(dw/128), ceil(dh/64), frames * 7): blockIdx.z is the plane job f*7+p, whose planes start
-// at job * stride in both levels. Warp wy of a CTA produces output rows (blockIdx.y*4 + wy)*16 .. +15.
+// block (32, 4); grid (ceil(dw/128), ceil(dh/(4 R)), frames * 7): blockIdx.z is the plane job f*7+p, whose planes start
+// at job * stride in both levels. Warp wy of a CTA produces output rows (blockIdx.y*4 + wy)*R .. +R-1. R = 16 on the large
+// levels (every source row is filtered once per 16 output rows); the small levels, whose grids would not fill the GPU and
+// whose walks are pure latency, use R = 4: four times the warps, each a quarter as long.
+template <int R>
 __global__ void __launch_bounds__(128, 12)      // 40 registers: the walk is latency-bound, residency pays more than the few spills
 k_pyr_down_roll(const float* __restrict__ src, int sw, int sh, int spitch, size_t sstride, float* __restrict__ dst, int dw,
                 int dh, int dpitch, size_t dstride) {
     const int job = blockIdx.z, p = job % 7, lane = threadIdx.x;
-    const int y0 = (blockIdx.y * 4 + threadIdx.y) * DN_R;
+    const int y0 = (blockIdx.y * 4 + threadIdx.y) * R;
     if (y0 >= dh) return;
     const float* __restrict__ sp = src + (size_t)job * sstride;
     float* __restrict__ dp = dst + (size_t)job * dstride;
     const DownSel sel(sw, dw);
-    const bool rows_in = 2 * y0 - 2 >= 0 && 2 * (y0 + DN_R - 1) + 2 <= sh - 1 && y0 + DN_R <= dh;
+    const bool rows_in = 2 * y0 - 2 >= 0 && 2 * (y0 + R - 1) + 2 <= sh - 1 && y0 + R <= dh;
 #pragma unroll 1
     for (int j = 0; j < 2; ++j) {
         const int xo = blockIdx.x * 128 + 64 * j + 2 * lane;
         const unsigned flags = down_pair_flags(sel, xo, p < 6, p % 3);
         if (__all_sync(FULL, rows_in && down_pair_interior(xo, sw, dw, flags)))
-            down_chunk_f32<true>(sp, sw, sh, spitch, dp, dw, dh, dpitch, xo, y0, lane, flags);
+            down_chunk_f32<true, R>(sp, sw, sh, spitch, dp, dw, dh, dpitch, xo, y0, lane, flags);
         else if (xo < dw)
-            down_chunk_f32<false>(sp, sw, sh, spitch, dp, dw, dh, dpitch, xo, y0, lane, flags);
+            down_chunk_f32<false, R>(sp, sw, sh, spitch, dp, dw, dh, dpitch, xo, y0, lane, flags);
     }
 }
 
@@ -382,33 +386,6 @@ struct __align__(128) Down0Ring {
     unsigned long long bar[D0_NS];
 };
 constexpr size_t D0_SMEM = sizeof(Down0Ring) * 3;
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    // try_wait with a suspend-time hint: a warp whose stage has not landed yet is parked by the hardware instead of
-    // spinning through the issue slots of the warps that have work
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "POPPY_MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-        "@p bra POPPY_MBAR_DONE;\n"
-        "bra POPPY_MBAR_WAIT;\n"
-        "POPPY_MBAR_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
-}
-// global -> shared bulk copy (bytes: multiple of 16; both addresses 16-byte aligned), completion on `bar`
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 // Producer side of one warp's ring: `seg0` points at element (row 2*y0 - 2, column 2*X0 - 4) of the role's source plane.
 template <class T>
@@ -846,7 +823,8 @@ __device__ __forceinline__ void emit_rows_generic(EmitCtx& E, int k, const float
 // One warp = one colour channel c of a 128 x 32 fine tile. `stages`: this warp's CL_STAGES staging slots.
 template <bool L0, bool INTERIOR, bool BULK = false, bool EMIT = false>
 __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int fx, int cy0, CollapseStage* stages, int lane,
-                                              CollapseBulkRing* ring = nullptr, EmitCtx* E = nullptr, bool emit_words = false) {
+                                              CollapseBulkRing* ring = nullptr, EmitCtx* E = nullptr, bool emit_words = false,
+                                              int R = CL_R) {
     const float* __restrict__ pl = A.gc + (size_t)c * A.cstride;
     const float* __restrict__ pr = A.gc + (size_t)(3 + c) * A.cstride;
     const float* __restrict__ po = A.oc + (size_t)c * A.cstride;
@@ -860,7 +838,7 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
     };
     // request step k's loads (coarse row cy0+k+1, fine rows 2(cy0+k), 2(cy0+k)+1) into its staging slot
     auto issue = [&](int k) {
-        if (k < CL_R) {
+        if (k < R) {
             CollapseStage& S = stages[k % CL_STAGES];
             const size_t coff = (size_t)(cy0 + k + 1) * A.cpitch + (fx >> 1);
             const float* __restrict__ cpl[3] = {pl + coff, pr + coff, po + coff};
@@ -891,7 +869,7 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
     // the same request as TMA row segments (lane 0 only); fx0 / a0: first fine / coarse column of the warp's tile
     const int fx0 = fx - 4 * lane, a0 = fx0 >> 1;
     auto issue_bulk = [&](int k) {
-        if (k < CL_R) {
+        if (k < R) {
             CollapseBulkStage& S = ring->st[k % CL_BULK_STAGES];
             unsigned long long* bar = &ring->bar[k % CL_BULK_STAGES];
             mbar_expect_tx(bar, CL_BULK_BYTES);
@@ -940,7 +918,7 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
     float* __restrict__ orow = EMIT ? nullptr : A.out + (size_t)c * A.ostride + (size_t)(2 * cy0) * A.opitch + fx;
     int k_done = 0;
 #pragma unroll 1
-    for (int k = 0; k < CL_R; ++k) {
+    for (int k = 0; k < R; ++k) {
         const int sy = cy0 + k, fy = 2 * sy;
         if (!INTERIOR && fy >= A.h) break;
         k_done = k + 1;
@@ -1045,12 +1023,12 @@ k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride,
                 const float* __restrict__ g_coarse, const float* __restrict__ out_coarse, int cw, int ch, int cpitch,
                 size_t cstride, float* __restrict__ out_fine, int opitch, size_t ostride, int use_bulk,
                 const unsigned char* __restrict__ tile_flags, const FrameParams* __restrict__ fp, uint8_t* __restrict__ frames_base,
-                size_t frame_bytes, unsigned char* __restrict__ ex, int ex_pitch, size_t ex_stride) {
+                size_t frame_bytes, unsigned char* __restrict__ ex, int ex_pitch, size_t ex_stride, int R) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     CollapseStage* stages = reinterpret_cast<CollapseStage*>(smem_dyn) + CL_STAGES * threadIdx.y;
     const int f = blockIdx.z, c = threadIdx.y;
     if (tile_flags && !tile_flags[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
-    const int fx = blockIdx.x * 128 + 4 * threadIdx.x, cy0 = blockIdx.y * CL_R;
+    const int fx = blockIdx.x * 128 + 4 * threadIdx.x, cy0 = blockIdx.y * R;
     CollapseArgs A;
     A.w1 = L0 ? warped + (size_t)f * 2 * wstride : nullptr; A.w2 = L0 ? A.w1 + wstride : nullptr; A.wpitch = wpitch;
     A.mask0 = L0 ? mask0 + (size_t)f * m0stride : nullptr; A.mpitch = mpitch;
@@ -1069,7 +1047,7 @@ k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride,
     }
     const int a = fx >> 1;
     const bool lane_in = a >= 1 && a + 2 <= cw - 1;                       // implies fx + 3 < w
-    const bool rows_in = cy0 >= 1 && cy0 + CL_R <= ch - 1 && 2 * (cy0 + CL_R) <= h;
+    const bool rows_in = cy0 >= 1 && cy0 + R <= ch - 1 && 2 * (cy0 + R) <= h;
     if (__all_sync(FULL, lane_in && rows_in)) {
         // TMA staging where the tile's 72-column coarse segment and 128-column fine segments lie inside their rows
         const int a0 = blockIdx.x * 64;
@@ -1077,11 +1055,11 @@ k_collapse_roll(const uint32_t* __restrict__ warped, int wpitch, size_t wstride,
                              (!L0 || (int)blockIdx.x * 128 + 128 <= mpitch);
         if (bulk_ok)
             collapse_body<L0, true, true, EMIT>(A, c, fx, cy0, stages, threadIdx.x, reinterpret_cast<CollapseBulkRing*>(smem_dyn) + threadIdx.y,
-                                                &E, emit_words);
+                                                &E, emit_words, R);
         else
-            collapse_body<L0, true, false, EMIT>(A, c, fx, cy0, stages, threadIdx.x, nullptr, &E, emit_words);
+            collapse_body<L0, true, false, EMIT>(A, c, fx, cy0, stages, threadIdx.x, nullptr, &E, emit_words, R);
     } else if (fx < w) {
-        collapse_body<L0, false, false, EMIT>(A, c, fx, cy0, stages, threadIdx.x, nullptr, &E, false);
+        collapse_body<L0, false, false, EMIT>(A, c, fx, cy0, stages, threadIdx.x, nullptr, &E, false, R);
     }
 }
 
@@ -1109,20 +1087,10 @@ struct CtBars { unsigned long long full[CT_NS], empty[CT_NS]; };
 template <bool L0> __host__ __device__ constexpr unsigned ct_stage_bytes() { return (L0 ? 2 * 2 * 128 * 4 + 2 * 128 * 4 : 7 * 2 * 128 * 4) + 6 * 72 * 4 + 3 * 72 * 4; }
 template <bool L0, bool EMIT> constexpr size_t ct_smem() { return CT_NS * sizeof(CtStage<L0>) + 128 + (EMIT ? 2 * 2 * 384 : 0); }
 
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const TmaMap* map, int x, int y, int z, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // channel warp c of an interior tile
 template <bool L0, bool EMIT>
 __device__ __forceinline__ void collapse_consume(const CollapseArgs& A, int c, int fx, int cy0, int lane, const CtStage<L0>* stages,
-                                                 CtBars* bars, EmitCtx* E, bool emit_words) {
+                                                 CtBars* bars, EmitCtx* E, bool emit_words, int R) {
     const float2 nz = c_negzero2;
     const float* __restrict__ pl = A.gc + (size_t)c * A.cstride;
     const float* __restrict__ pr = A.gc + (size_t)(3 + c) * A.cstride;
@@ -1136,7 +1104,7 @@ __device__ __forceinline__ void collapse_consume(const CollapseArgs& A, int c, i
     }
     float* __restrict__ orow = EMIT ? nullptr : A.out + (size_t)c * A.ostride + (size_t)(2 * cy0) * A.opitch + fx;
 #pragma unroll 1
-    for (int k = 0; k < CL_R; ++k) {
+    for (int k = 0; k < R; ++k) {
         const int s = k % CT_NS, fy = 2 * (cy0 + k);
         mbar_wait(&bars->full[s], (unsigned)(k / CT_NS) & 1u);
         const CtStage<L0>& S = stages[s];
@@ -1209,11 +1177,11 @@ k_collapse_tma(const __grid_constant__ TmaMap tm_fine, const __grid_constant__ T
                size_t fstride, const float* __restrict__ g_coarse, const float* __restrict__ out_coarse, int cw, int ch, int cpitch,
                size_t cstride, float* __restrict__ out_fine, int opitch, size_t ostride, const unsigned char* __restrict__ tile_flags,
                const FrameParams* __restrict__ fp, uint8_t* __restrict__ frames_base, size_t frame_bytes, unsigned char* __restrict__ ex,
-               int ex_pitch, size_t ex_stride, int map_frame0) {
+               int ex_pitch, size_t ex_stride, int map_frame0, int R) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     const int f = blockIdx.z, warp = threadIdx.y, lane = threadIdx.x, c = warp < 3 ? warp : 0;
     if (tile_flags && !tile_flags[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
-    const int fx = blockIdx.x * 128 + 4 * lane, cy0 = blockIdx.y * CL_R;
+    const int fx = blockIdx.x * 128 + 4 * lane, cy0 = blockIdx.y * R;
     CollapseArgs A;
     A.w1 = L0 ? warped + (size_t)f * 2 * wstride : nullptr; A.w2 = L0 ? A.w1 + wstride : nullptr; A.wpitch = wpitch;
     A.mask0 = L0 ? mask0 + (size_t)f * m0stride : nullptr; A.mpitch = mpitch;
@@ -1234,7 +1202,7 @@ k_collapse_tma(const __grid_constant__ TmaMap tm_fine, const __grid_constant__ T
     }
     const int a = fx >> 1;
     const bool lane_in = a >= 1 && a + 2 <= cw - 1;                       // implies fx + 3 < w
-    const bool rows_in = cy0 >= 1 && cy0 + CL_R <= ch - 1 && 2 * (cy0 + CL_R) <= h;
+    const bool rows_in = cy0 >= 1 && cy0 + R <= ch - 1 && 2 * (cy0 + R) <= h;
     if (__all_sync(FULL, lane_in && rows_in)) {                           // the same decision in all four warps
         if (warp == 3 && lane == 0) {
 #pragma unroll
@@ -1246,7 +1214,7 @@ k_collapse_tma(const __grid_constant__ TmaMap tm_fine, const __grid_constant__ T
             if (lane == 0) {
                 const int fx0 = blockIdx.x * 128, a0 = fx0 >> 1, mf = map_frame0 + f;      // the maps span the whole chunk
 #pragma unroll 1
-                for (int k = 0; k < CL_R; ++k) {
+                for (int k = 0; k < R; ++k) {
                     const int s = k % CT_NS;
                     if (k >= CT_NS) mbar_wait(&bars->empty[s], (unsigned)(k / CT_NS - 1) & 1u);
                     // the channel warps read the stage through the generic proxy; order those reads before the TMA writes
@@ -1268,9 +1236,9 @@ k_collapse_tma(const __grid_constant__ TmaMap tm_fine, const __grid_constant__ T
             }
             return;
         }
-        collapse_consume<L0, EMIT>(A, c, fx, cy0, lane, stages, bars, &E, emit_words);
+        collapse_consume<L0, EMIT>(A, c, fx, cy0, lane, stages, bars, &E, emit_words, R);
     } else if (warp < 3 && fx < w) {
-        collapse_body<L0, false, false, EMIT>(A, c, fx, cy0, nullptr, lane, nullptr, &E, false);
+        collapse_body<L0, false, false, EMIT>(A, c, fx, cy0, nullptr, lane, nullptr, &E, false, R);
     }
 }
 
@@ -1303,8 +1271,14 @@ void launch_pyr_down0(cudaStream_t st, const uint32_t* warped, int wpitch, size_
 }
 
 void launch_pyr_down(cudaStream_t st, const float* src, LevelDesc sl, float* dst, LevelDesc dl, int frames) {
-    k_pyr_down_roll<<<dim3(div_up(dl.w, 128), div_up(dl.h, 4 * DN_R), frames * 7), dim3(32, 4), 0, st>>>(
-        src, sl.w, sl.h, sl.pitch, sl.plane_stride, dst, dl.w, dl.h, dl.pitch, dl.plane_stride);
+    // a grid of 16-row walks that cannot give every SM a few CTAs is cut into 4-row walks instead
+    const long long ctas16 = (long long)div_up(dl.w, 128) * div_up(dl.h, 4 * DN_R) * frames * 7;
+    if (ctas16 < 148 * 12)
+        k_pyr_down_roll<4><<<dim3(div_up(dl.w, 128), div_up(dl.h, 4 * 4), frames * 7), dim3(32, 4), 0, st>>>(
+            src, sl.w, sl.h, sl.pitch, sl.plane_stride, dst, dl.w, dl.h, dl.pitch, dl.plane_stride);
+    else
+        k_pyr_down_roll<DN_R><<<dim3(div_up(dl.w, 128), div_up(dl.h, 4 * DN_R), frames * 7), dim3(32, 4), 0, st>>>(
+            src, sl.w, sl.h, sl.pitch, sl.plane_stride, dst, dl.w, dl.h, dl.pitch, dl.plane_stride);
 }
 
 void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* out, int frames) {
@@ -1321,20 +1295,25 @@ static bool use_tma() {
 
 void launch_collapse(cudaStream_t st, const float* g_fine, LevelDesc fl, const float* g_coarse, const float* out_coarse,
                      LevelDesc cl, float* out_fine, int frames, const CollapseMaps* maps) {
-    const dim3 grid(div_up(fl.w, 128), div_up(fl.h, 2 * CL_R), frames);
+    // coarse rows per warp: 16 on the large levels; a grid of 16-row walks that cannot give every SM a few CTAs is cut into
+    // 4-row walks (the small levels are pure latency: four times the warps, each a quarter as long)
+    const long long ctas16 = (long long)div_up(fl.w, 128) * div_up(fl.h, 2 * CL_R) * frames;
+    const int R = ctas16 < 148 * 12 ? 4 : CL_R;
+    const dim3 grid(div_up(fl.w, 128), div_up(fl.h, 2 * R), frames);
     if (maps && use_tma()) {
         static SmemAttrOnce done;
         ensure_smem_attr(k_collapse_tma<false, false>, ct_smem<false, false>(), done);
         k_collapse_tma<false, false><<<grid, dim3(32, 4), ct_smem<false, false>(), st>>>(
             maps->fine, maps->mask, maps->gc, maps->oc, nullptr, 0, 0, nullptr, 0, 0, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse,
-            out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, out_fine, fl.pitch, fl.plane_stride, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, 0);
+            out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, out_fine, fl.pitch, fl.plane_stride, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, 0,
+            R);
         return;
     }
     static SmemAttrOnce done;
     ensure_smem_attr(k_collapse_roll<false, false>, CL_SMEM, done);
     k_collapse_roll<false, false><<<grid, dim3(32, 3), CL_SMEM, st>>>(
         nullptr, 0, 0, nullptr, 0, 0, g_fine, fl.w, fl.h, fl.pitch, fl.plane_stride, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
-        cl.plane_stride, out_fine, fl.pitch, fl.plane_stride, collapse_bulk_mode() & 2 ? 1 : 0, nullptr, nullptr, nullptr, 0, nullptr, 0, 0);
+        cl.plane_stride, out_fine, fl.pitch, fl.plane_stride, collapse_bulk_mode() & 2 ? 1 : 0, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, R);
 }
 
 void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
@@ -1348,7 +1327,7 @@ void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_
         k_collapse_tma<true, false><<<grid, dim3(32, 4), ct_smem<true, false>(), st>>>(
             maps->fine, maps->mask, maps->gc, maps->oc, warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse,
             out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, out_fine, ol.pitch, ol.plane_stride, tile_flags, nullptr, nullptr, 0, nullptr,
-            0, 0, map_frame0);
+            0, 0, map_frame0, CL_R);
         return;
     }
     static SmemAttrOnce done;
@@ -1356,7 +1335,7 @@ void launch_collapse0(cudaStream_t st, const uint32_t* warped, int wpitch, size_
     k_collapse_roll<true, false><<<grid, dim3(32, 3), CL_SMEM, st>>>(
         warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
         cl.plane_stride, out_fine, ol.pitch, ol.plane_stride, collapse_bulk_mode() & 1 ? 1 : 0, tile_flags, nullptr, nullptr, 0, nullptr,
-        0, 0);
+        0, 0, CL_R);
 }
 
 void launch_collapse0_emit(cudaStream_t st, const uint32_t* warped, int wpitch, size_t wstride, const float* mask0, int mpitch,
@@ -1369,7 +1348,8 @@ void launch_collapse0_emit(cudaStream_t st, const uint32_t* warped, int wpitch, 
         ensure_smem_attr(k_collapse_tma<true, true>, ct_smem<true, true>(), done);
         k_collapse_tma<true, true><<<grid, dim3(32, 4), ct_smem<true, true>(), st>>>(
             maps->fine, maps->mask, maps->gc, maps->oc, warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse,
-            out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, nullptr, 0, 0, nullptr, fp, frames_base, frame_bytes, ex, ex_pitch, ex_stride, 0);
+            out_coarse, cl.w, cl.h, cl.pitch, cl.plane_stride, nullptr, 0, 0, nullptr, fp, frames_base, frame_bytes, ex, ex_pitch, ex_stride, 0,
+            CL_R);
         return;
     }
     static SmemAttrOnce done;
@@ -1377,7 +1357,7 @@ void launch_collapse0_emit(cudaStream_t st, const uint32_t* warped, int wpitch, 
     k_collapse_roll<true, true><<<grid, dim3(32, 3), CL_EMIT_SMEM, st>>>(
         warped, wpitch, wstride, mask0, mpitch, m0stride, nullptr, w, h, 0, 0, g_coarse, out_coarse, cl.w, cl.h, cl.pitch,
         cl.plane_stride, nullptr, 0, 0, collapse_bulk_mode() & 1 ? 1 : 0, nullptr, fp, frames_base, frame_bytes, ex, ex_pitch,
-        ex_stride);
+        ex_stride, CL_R);
 }
 
 }  // namespace poppy

@@ -35,6 +35,14 @@ const char* const kClassNames[KC_COUNT] = {"lerp_points", "tri_geometry", "bin_t
 
 struct TimedLaunch { int cls; cudaEvent_t a, b; };
 
+// Adaptive routing of the unsharp stage (unsharp_mode 0): calm route while at most this share of the strip chunks of recent
+// frames needed (or, on the dense route, would have needed) the exact path; the dense route otherwise. On the dense route
+// every kCalmProbeEvery-th chunk also runs the calm analysis on its finished frames - a few percent of a chunk's time - so
+// that the router notices when the content calms down again. (Break-even: the calm route costs about half of the dense one
+// plus 1.4x the dense cost of whatever it flags.)
+constexpr double kCalmRouteMaxShare = 0.2;
+constexpr unsigned kCalmProbeEvery = 8;      // on the dense route: every n-th chunk also runs the (cheap) byte scan for the statistic
+
 // rows per CTA of the exact unsharp pass over flagged strip chunks (the dense pass used 216; a finer grain keeps calm
 // regions out of the exact path at the price of the 10-row warm-up per chunk)
 constexpr int kSparseChunkRows = 24;
@@ -113,8 +121,8 @@ struct poppy_cuda_ctx {
     int unsharp_mode = 0;
     int l0_group = 0;                        // POPPY_CUDA_L0_GROUP: frames per (level-0 collapse, unsharp) launch pair of the dense route
     int l0_chunk_rows = 0;                   // POPPY_CUDA_US_ROWS: rows per CTA of the dense unsharp pass (0: 216)
-    double calm_share = 0.0;                 // running share of flagged strip chunks on the calm route
-    unsigned route_tick = 0;
+    double calm_share = 1.0;                 // running share of flagged strip chunks (starts pessimistic: dense until a scan says otherwise)
+    unsigned route_tick = kCalmProbeEvery - 1;   // the first dense chunk carries a scan
     int mm_pitch = 0;                        // blocks per row of the clamp-excess table, padded
     size_t mm_stride = 0;
     unsigned long long* d_calm_total = nullptr;      // flagged strip chunks since the last stats read
@@ -316,14 +324,6 @@ void collect_timing(poppy_cuda_ctx* c) {
     }
     c->timed.clear();
 }
-
-// Adaptive routing of the unsharp stage (unsharp_mode 0): calm route while at most this share of the strip chunks of recent
-// frames needed (or, on the dense route, would have needed) the exact path; the dense route otherwise. On the dense route
-// every kCalmProbeEvery-th chunk also runs the calm analysis on its finished frames - a few percent of a chunk's time - so
-// that the router notices when the content calms down again. (Break-even: the calm route costs about half of the dense one
-// plus 1.4x the dense cost of whatever it flags.)
-constexpr double kCalmRouteMaxShare = 0.25;
-constexpr unsigned kCalmProbeEvery = 4;      // on the dense route: every n-th chunk also runs the (cheap) byte scan for the statistic
 
 // fold the flagged-chunk counts of finished calm-route chunks into the running share (never blocks unless `wait`)
 void harvest_calm_stats(poppy_cuda_ctx* c, bool wait) {
@@ -984,8 +984,7 @@ int poppy_cuda_debug_read(poppy_cuda_ctx* c, int stage, int frame, void* dst, si
         std::vector<TriInverse> tmp(std::max(P.n_tri, 1));
         CU_TRY(c, cudaMemcpy(tmp.data(), c->lane[0].d_inv, (size_t)P.n_tri * sizeof(TriInverse), cudaMemcpyDeviceToHost));
         float* o = (float*)dst;
-        for (int i = 0; i < P.n_tri; ++i)
-            for (int j = 0; j < 9; ++j) o[9 * i + j] = stage == POPPY_STAGE_INV_M1 ? tmp[i].m[j].x : tmp[i].m[j].y;
+        for (int i = 0; i < P.n_tri; ++i) std::memcpy(o + 9 * i, stage == POPPY_STAGE_INV_M1 ? tmp[i].a : tmp[i].b, 36);
         return 0;
     }
     case POPPY_STAGE_WARPED1:
