@@ -66,6 +66,10 @@ void launch_pyr_down0(cudaStream_t st, const uint32_t* warped, int wpitch, size_
                       int frames);
 // level k -> k+1 for the 7 planes (left BGR, right BGR, mask)
 void launch_pyr_down(cudaStream_t st, const float* src, LevelDesc sl, float* dst, LevelDesc dl, int frames);
+// Levels k0 .. L of a chunk in one launch (one CTA per frame): pyrDown k0 -> ... -> L, resultSmallest, collapse L-1 .. k0.
+// levels[k]: geometry of level k and the float offsets of its first plane inside the chunk's Gaussian / out blocks.
+struct TailLevel { int w, h, pitch, pad; size_t plane_stride, g_off, o_off; };
+void launch_pyramid_tail(cudaStream_t st, float* g_base, float* o_base, const TailLevel* levels, int k0, int L, int frames);
 // resultSmallest = left*mask + right*(1-mask) at the coarsest level (blend.hpp:68-69)
 void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* out, int frames);
 // out[k] = pyrUp(out[k+1]) + (G_l[k]-pyrUp(G_l[k+1]))*m[k] + (G_r[k]-pyrUp(G_r[k+1]))*(1-m[k])   (blend.hpp:45-77)

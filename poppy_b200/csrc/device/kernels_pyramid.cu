@@ -38,6 +38,11 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// Loads of the generic (border / tiny-level) bodies. CG = false: read-only path (data written by an earlier kernel).
+// CG = true: ld.global.ca instead of the non-coherent ld.global.nc - for k_pyramid_tail, where one CTA reads what it wrote
+// a level earlier (a CTA lives on one SM, whose L1 sees the CTA's own stores; the taps of a tiny level then hit L1).
+template <bool CG, class T> __device__ __forceinline__ T ld_in(const T* p) { return CG ? __ldca(p) : __ldg(p); }
+
 // horizontal 1-4-6-4-1, vector-body association: r2*6 + ((r1+r3)*4 + (r0+r4))
 __device__ __forceinline__ float h5_vec(float t0, float t1, float t2, float t3, float t4) {
     return __fadd_rn(__fmul_rn(t2, 6.f), __fadd_rn(__fmul_rn(__fadd_rn(t1, t3), 4.f), __fadd_rn(t0, t4)));
@@ -128,7 +133,7 @@ __device__ __forceinline__ void down_load(const float* __restrict__ plane, int s
 }
 
 // row pass of outputs xo, xo+1 of source row iy
-template <bool INTERIOR>
+template <bool INTERIOR, bool CG = false>
 __device__ __forceinline__ float2 down_rowpass(const float* __restrict__ plane, int spitch, int sw, int sh, int iy, int xo,
                                                int lane, const DownRaw& r, bool va, bool vb, bool has_b) {
     if (INTERIOR) {
@@ -141,13 +146,13 @@ __device__ __forceinline__ float2 down_rowpass(const float* __restrict__ plane, 
         const float* __restrict__ row = plane + (size_t)reflect101(iy, sh) * spitch;
         float t[5];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) t[j] = __ldg(row + reflect101(2 * xo - 2 + j, sw));
+        for (int j = 0; j < 5; ++j) t[j] = ld_in<CG>(row + reflect101(2 * xo - 2 + j, sw));
         float2 o;
         o.x = va ? h5_vec(t[0], t[1], t[2], t[3], t[4]) : h5_sca(t[0], t[1], t[2], t[3], t[4]);
         o.y = 0.f;
         if (has_b) {
 #pragma unroll
-            for (int j = 0; j < 5; ++j) t[j] = __ldg(row + reflect101(2 * xo + j, sw));
+            for (int j = 0; j < 5; ++j) t[j] = ld_in<CG>(row + reflect101(2 * xo + j, sw));
             o.y = vb ? h5_vec(t[0], t[1], t[2], t[3], t[4]) : h5_sca(t[0], t[1], t[2], t[3], t[4]);
         }
         return o;
@@ -156,7 +161,7 @@ __device__ __forceinline__ float2 down_rowpass(const float* __restrict__ plane, 
 
 // One chunk (64 output columns) x DN_R output rows of one plane. Flags: bit 0/1 = vector-body association of the row
 // pass at xo / xo+1, bit 2/3 = of the column pass.
-template <bool INTERIOR, int R = DN_R>
+template <bool INTERIOR, int R = DN_R, bool CG = false>
 __device__ __forceinline__ void down_chunk_f32(const float* __restrict__ sp, int sw, int sh, int spitch, float* __restrict__ dp,
                                                int dw, int dh, int dpitch, int xo, int y0, int lane, unsigned flags) {
     const bool ha = flags & 1u, hb = flags & 2u, va = flags & 4u, vb = flags & 8u, has_b = INTERIOR || xo + 1 < dw;
@@ -164,10 +169,10 @@ __device__ __forceinline__ void down_chunk_f32(const float* __restrict__ sp, int
     DownRaw ra, rb;
     down_load<INTERIOR>(sp, spitch, sh, 2 * y0 - 2, xo, lane, ra);
     down_load<INTERIOR>(sp, spitch, sh, 2 * y0 - 1, xo, lane, rb);
-    h0 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y0 - 2, xo, lane, ra, ha, hb, has_b);
-    h1 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y0 - 1, xo, lane, rb, ha, hb, has_b);
+    h0 = down_rowpass<INTERIOR, CG>(sp, spitch, sw, sh, 2 * y0 - 2, xo, lane, ra, ha, hb, has_b);
+    h1 = down_rowpass<INTERIOR, CG>(sp, spitch, sw, sh, 2 * y0 - 1, xo, lane, rb, ha, hb, has_b);
     down_load<INTERIOR>(sp, spitch, sh, 2 * y0, xo, lane, ra);
-    h2 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y0, xo, lane, ra, ha, hb, has_b);
+    h2 = down_rowpass<INTERIOR, CG>(sp, spitch, sw, sh, 2 * y0, xo, lane, ra, ha, hb, has_b);
     // software pipeline: the two source rows of output row y+1 are requested before output row y is computed
     down_load<INTERIOR>(sp, spitch, sh, 2 * y0 + 1, xo, lane, ra);
     down_load<INTERIOR>(sp, spitch, sh, 2 * y0 + 2, xo, lane, rb);
@@ -175,8 +180,8 @@ __device__ __forceinline__ void down_chunk_f32(const float* __restrict__ sp, int
     for (int k = 0; k < R; ++k) {
         const int y = y0 + k;
         if (!INTERIOR && y >= dh) break;
-        h3 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y + 1, xo, lane, ra, ha, hb, has_b);
-        h4 = down_rowpass<INTERIOR>(sp, spitch, sw, sh, 2 * y + 2, xo, lane, rb, ha, hb, has_b);
+        h3 = down_rowpass<INTERIOR, CG>(sp, spitch, sw, sh, 2 * y + 1, xo, lane, ra, ha, hb, has_b);
+        h4 = down_rowpass<INTERIOR, CG>(sp, spitch, sw, sh, 2 * y + 2, xo, lane, rb, ha, hb, has_b);
         if (k + 1 < R) {
             down_load<INTERIOR>(sp, spitch, sh, 2 * y + 3, xo, lane, ra);
             down_load<INTERIOR>(sp, spitch, sh, 2 * y + 4, xo, lane, rb);
@@ -580,22 +585,23 @@ namespace {
 constexpr int CL_R = 16;           // coarse rows per warp of the collapse kernel (32 fine rows x 128 fine columns)
 
 // horizontal pass of cv::pyrUp at fine column x of one coarse row of n pixels (pyramids.cpp:945-978)
+template <bool CG = false>
 __device__ __forceinline__ float up_h(const float* __restrict__ row, int n, int x) {
     const int sx = x >> 1;
-    if (n == 1) return __fmul_rn(__ldg(row), 8.f);
+    if (n == 1) return __fmul_rn(ld_in<CG>(row), 8.f);
     if (x & 1) {
-        if (sx == n - 1) return __fmul_rn(__ldg(row + n - 1), 8.f);
-        return __fmul_rn(__fadd_rn(__ldg(row + sx), __ldg(row + sx + 1)), 4.f);
+        if (sx == n - 1) return __fmul_rn(ld_in<CG>(row + n - 1), 8.f);
+        return __fmul_rn(__fadd_rn(ld_in<CG>(row + sx), ld_in<CG>(row + sx + 1)), 4.f);
     }
-    if (sx == 0) return __fadd_rn(__fmul_rn(__ldg(row), 6.f), __fmul_rn(__ldg(row + 1), 2.f));
-    if (sx == n - 1) return __fadd_rn(__ldg(row + n - 2), __fmul_rn(__ldg(row + n - 1), 7.f));
-    return __fadd_rn(__fadd_rn(__ldg(row + sx - 1), __fmul_rn(__ldg(row + sx), 6.f)), __ldg(row + sx + 1));
+    if (sx == 0) return __fadd_rn(__fmul_rn(ld_in<CG>(row), 6.f), __fmul_rn(ld_in<CG>(row + 1), 2.f));
+    if (sx == n - 1) return __fadd_rn(ld_in<CG>(row + n - 2), __fmul_rn(ld_in<CG>(row + n - 1), 7.f));
+    return __fadd_rn(__fadd_rn(ld_in<CG>(row + sx - 1), __fmul_rn(ld_in<CG>(row + sx), 6.f)), ld_in<CG>(row + sx + 1));
 }
 
 // Row pass of cv::pyrUp for the 4 fine columns fx..fx+3 (coarse columns a = fx/2, a+1) of one coarse row, scaled by 1/64.
 // Scaling by a power of two is exact and commutes with every rounding of the column pass, so applying it here instead of
 // after the column sums (pyramids.cpp:989-991) is bit-identical and saves one multiply per value and fine row.
-template <bool INTERIOR>
+template <bool INTERIOR, bool CG = false>
 __device__ __forceinline__ void up_row(const float* __restrict__ row, int cw, int w, int fx, float (&o)[4]) {
     if (INTERIOR) {
         const float* __restrict__ p = row + (fx >> 1);
@@ -608,7 +614,7 @@ __device__ __forceinline__ void up_row(const float* __restrict__ row, int cw, in
         o[3] = __fmul_rn(__fadd_rn(c01.y, cp), 4.f);
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = fx + i < w ? up_h(row, cw, fx + i) : 0.f;
+        for (int i = 0; i < 4; ++i) o[i] = fx + i < w ? up_h<CG>(row, cw, fx + i) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i] = __fmul_rn(o[i], 1.f / 64);
@@ -725,6 +731,13 @@ __device__ __forceinline__ void fine_load<false>(const CollapseArgs& A, int c, i
     r.r = __ldg(reinterpret_cast<const float4*>(gp + (size_t)(3 + c) * A.fstride));
     r.m = __ldg(reinterpret_cast<const float4*>(gp + (size_t)6 * A.fstride));
 }
+// the same through the coherent path (k_pyramid_tail)
+__device__ __forceinline__ void fine_load_cg(const CollapseArgs& A, int c, int fy, int fx, FineRaw<false>& r) {
+    const float* gp = A.gfine + (size_t)fy * A.fpitch + fx;
+    r.l = __ldca(reinterpret_cast<const float4*>(gp + (size_t)c * A.fstride));
+    r.r = __ldca(reinterpret_cast<const float4*>(gp + (size_t)(3 + c) * A.fstride));
+    r.m = __ldca(reinterpret_cast<const float4*>(gp + (size_t)6 * A.fstride));
+}
 __device__ __forceinline__ void fine_unpack(const FineRaw<true>& r, int c, float (&gl)[4], float (&gr)[4], float (&mk)[4]) {
     gl[0] = unit_from_byte(r.a.x, c); gl[1] = unit_from_byte(r.a.y, c); gl[2] = unit_from_byte(r.a.z, c); gl[3] = unit_from_byte(r.a.w, c);
     gr[0] = unit_from_byte(r.b.x, c); gr[1] = unit_from_byte(r.b.y, c); gr[2] = unit_from_byte(r.b.z, c); gr[3] = unit_from_byte(r.b.w, c);
@@ -821,7 +834,7 @@ __device__ __forceinline__ void emit_rows_generic(EmitCtx& E, int k, const float
 }
 
 // One warp = one colour channel c of a 128 x 32 fine tile. `stages`: this warp's CL_STAGES staging slots.
-template <bool L0, bool INTERIOR, bool BULK = false, bool EMIT = false>
+template <bool L0, bool INTERIOR, bool BULK = false, bool EMIT = false, bool CG = false>
 __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int fx, int cy0, CollapseStage* stages, int lane,
                                               CollapseBulkRing* ring = nullptr, EmitCtx* E = nullptr, bool emit_words = false,
                                               int R = CL_R) {
@@ -832,9 +845,9 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
     float hm[3][4], h0[3][4], hp[3][4];          // row-pass values of coarse rows sy-1, sy, sy+1 for (left, right, out)
     auto coarse_now = [&](int cy, float (&h)[3][4]) {            // load where consumed
         const size_t off = (size_t)cy * A.cpitch;
-        up_row<INTERIOR>(pl + off, A.cw, A.w, fx, h[0]);
-        up_row<INTERIOR>(pr + off, A.cw, A.w, fx, h[1]);
-        up_row<INTERIOR>(po + off, A.cw, A.w, fx, h[2]);
+        up_row<INTERIOR, CG>(pl + off, A.cw, A.w, fx, h[0]);
+        up_row<INTERIOR, CG>(pr + off, A.cw, A.w, fx, h[1]);
+        up_row<INTERIOR, CG>(po + off, A.cw, A.w, fx, h[2]);
     };
     // request step k's loads (coarse row cy0+k+1, fine rows 2(cy0+k), 2(cy0+k)+1) into its staging slot
     auto issue = [&](int k) {
@@ -963,10 +976,10 @@ __device__ __forceinline__ void collapse_body(const CollapseArgs& A, int c, int 
         } else {
             FineRaw<L0> rf;
             coarse_now(min(sy + 1, A.ch - 1), hp);
-            fine_load<L0>(A, c, fy, fx, rf);
+            if (CG) fine_load_cg(A, c, fy, fx, reinterpret_cast<FineRaw<false>&>(rf)); else fine_load<L0>(A, c, fy, fx, rf);
             fine_unpack(rf, c, gl[0], gr[0], mk[0]);
             if (two) {
-                fine_load<L0>(A, c, fy + 1, fx, rf);
+                if (CG) fine_load_cg(A, c, fy + 1, fx, reinterpret_cast<FineRaw<false>&>(rf)); else fine_load<L0>(A, c, fy + 1, fx, rf);
                 fine_unpack(rf, c, gl[1], gr[1], mk[1]);
             }
         }
@@ -1242,6 +1255,68 @@ k_collapse_tma(const __grid_constant__ TmaMap tm_fine, const __grid_constant__ T
     }
 }
 
+// ---- the tail of the pyramid in one launch ----------------------------------------------------------------------------
+// Settings::pyramid_levels defaults to 64 (reference src/settings.hpp:20): a 512 x 512 frame reaches 1 x 1 at level 9 and the
+// reference keeps calling pyrDown / pyrUp on 1 x 1 images for 55 more levels (OCV pyramids.cpp:945-950 handles them). Launching
+// two kernels per level makes a chained frame launch-latency bound (~130 launches). k_pyramid_tail runs every level from k0
+// (the first one no larger than 32 x 32) to L and back inside one CTA per frame: the same generic bodies as the per-level
+// kernels (bit-identical), block barriers between the levels, L2-coherent loads for what the CTA itself wrote.
+__global__ void __launch_bounds__(256)
+k_pyramid_tail(float* __restrict__ g_base, float* __restrict__ o_base, const TailLevel* __restrict__ lv, int k0, int L) {
+    const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Gaussian pyramids (7 planes) down to level L
+    for (int k = k0; k < L; ++k) {
+        const TailLevel S = lv[k], D = lv[k + 1];
+        const float* sb = g_base + S.g_off + (size_t)f * 7 * S.plane_stride;
+        float* db = g_base + D.g_off + (size_t)f * 7 * D.plane_stride;
+        const DownSel sel(S.w, D.w);
+        const int ncol = div_up(D.w, 64), nrow = div_up(D.h, 4), jobs = 7 * ncol * nrow;
+        for (int job = warp; job < jobs; job += 8) {
+            const int p = job % 7, rest = job / 7, xo = 64 * (rest % ncol) + 2 * lane, y0 = 4 * (rest / ncol);
+            const unsigned flags = down_pair_flags(sel, xo, p < 6, p % 3);
+            if (xo < D.w)
+                down_chunk_f32<false, 4, true>(sb + (size_t)p * S.plane_stride, S.w, S.h, S.pitch, db + (size_t)p * D.plane_stride, D.w, D.h,
+                                               D.pitch, xo, y0, lane, flags);
+        }
+        // while a level is one job per plane, plane p stays with warp p from level to level: no block barrier needed
+        if (jobs == 7 && k + 1 < L) __syncwarp(); else __syncthreads();
+    }
+    __syncthreads();
+    {   // resultSmallest (blend.hpp:68-69)
+        const TailLevel T = lv[L];
+        const float* gf = g_base + T.g_off + (size_t)f * 7 * T.plane_stride;
+        float* of = o_base + T.o_off + (size_t)f * 3 * T.plane_stride;
+        for (int i = threadIdx.x; i < T.w * T.h; i += 256) {
+            const size_t o = (size_t)(i / T.w) * T.pitch + (i % T.w);
+            const float m = __ldca(gf + 6 * T.plane_stride + o), anti = __fsub_rn(1.0f, m);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                of[(size_t)c * T.plane_stride + o] = __fadd_rn(__fmul_rn(__ldca(gf + (size_t)c * T.plane_stride + o), m),
+                                                               __fmul_rn(__ldca(gf + (size_t)(3 + c) * T.plane_stride + o), anti));
+        }
+        __syncthreads();
+    }
+    // collapse back up to level k0
+    for (int k = L - 1; k >= k0; --k) {
+        const TailLevel F = lv[k], Cc = lv[k + 1];
+        CollapseArgs A;
+        A.w1 = A.w2 = nullptr; A.wpitch = 0; A.mask0 = nullptr; A.mpitch = 0;
+        A.gfine = g_base + F.g_off + (size_t)f * 7 * F.plane_stride; A.fpitch = F.pitch; A.fstride = F.plane_stride;
+        A.gc = g_base + Cc.g_off + (size_t)f * 7 * Cc.plane_stride; A.oc = o_base + Cc.o_off + (size_t)f * 3 * Cc.plane_stride;
+        A.cw = Cc.w; A.ch = Cc.h; A.cpitch = Cc.pitch; A.cstride = Cc.plane_stride;
+        A.out = o_base + F.o_off + (size_t)f * 3 * F.plane_stride; A.opitch = F.pitch; A.ostride = F.plane_stride; A.w = F.w; A.h = F.h;
+        const int ncol = div_up(F.w, 128), nrow = div_up(F.h, 8), jobs = 3 * ncol * nrow;
+        for (int job = warp; job < jobs; job += 8) {
+            const int c = job % 3, rest = job / 3, fx = 128 * (rest % ncol) + 4 * lane, cy0 = 4 * (rest / ncol);
+            if (fx < F.w) collapse_body<false, false, false, false, true>(A, c, fx, cy0, nullptr, lane, nullptr, nullptr, false, 4);
+        }
+        // one job per channel: out[k] of channel c is written and read (as out_coarse of level k-1) by warp c; the Gaussian
+        // planes were all finished before the barrier that precedes the collapse
+        const int next_jobs = k > k0 ? 3 * div_up(lv[k - 1].w, 128) * div_up(lv[k - 1].h, 8) : 0;
+        if (jobs == 3 && next_jobs == 3) __syncwarp(); else __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // A/B switch for profiling: POPPY_CUDA_NO_BULK=1 selects the register-prefetch bodies everywhere
 static bool use_bulk() {
@@ -1279,6 +1354,10 @@ void launch_pyr_down(cudaStream_t st, const float* src, LevelDesc sl, float* dst
     else
         k_pyr_down_roll<DN_R><<<dim3(div_up(dl.w, 128), div_up(dl.h, 4 * DN_R), frames * 7), dim3(32, 4), 0, st>>>(
             src, sl.w, sl.h, sl.pitch, sl.plane_stride, dst, dl.w, dl.h, dl.pitch, dl.plane_stride);
+}
+
+void launch_pyramid_tail(cudaStream_t st, float* g_base, float* o_base, const TailLevel* levels, int k0, int L, int frames) {
+    k_pyramid_tail<<<frames, 256, 0, st>>>(g_base, o_base, levels, k0, L);
 }
 
 void launch_blend_coarsest(cudaStream_t st, const float* g, LevelDesc l, float* out, int frames) {

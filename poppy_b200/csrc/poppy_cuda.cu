@@ -114,6 +114,9 @@ struct poppy_cuda_ctx {
     int want_lanes = 3;                      // POPPY_CUDA_LANES (1..4)
     int n_lanes = 0;                         // lanes allocated (0 = none yet)
     int n_tiles = 0, list_cap = 0;
+    // levels tail_k0 .. L run in one launch (k_pyramid_tail); 0 = none (no level is small enough, or POPPY_CUDA_TAIL=0)
+    int tail_k0 = 0;
+    TailLevel* d_tail_levels = nullptr;
     // unsharp stage. Calm route: the fused level-0 collapse stores the frame and only the strip chunks that can reach the
     // unsharp threshold run the exact blur + median path. Dense route: level-0 collapse to float planes + the exact path on
     // every pixel. 0 = adaptive (the calm route while the share of flagged chunks seen on recent frames stays low, the dense
@@ -255,6 +258,15 @@ int ensure_chunk(poppy_cuda_ctx* c) {
     }
     c->chunk = want;
     c->n_lanes = lanes;
+    {   // level table of k_pyramid_tail: the offsets depend on the chunk size
+        std::vector<TailLevel> tl(c->levels + 1);
+        for (int k = 0; k <= c->levels; ++k)
+            tl[k] = TailLevel{c->lv[k].w, c->lv[k].h, c->lv[k].pitch, 0, c->lv[k].plane_stride, c->g_off[k] * (size_t)want, c->o_off[k] * (size_t)want};
+        cudaFree(c->d_tail_levels);
+        c->d_tail_levels = nullptr;
+        CU_TRY(c, dmalloc(&c->d_tail_levels, tl.size()));
+        CU_TRY(c, cudaMemcpy(c->d_tail_levels, tl.data(), tl.size() * sizeof(TailLevel), cudaMemcpyHostToDevice));
+    }
     // tensor maps of every level's collapse (level k fine, level k+1 coarse); a level whose maps cannot be built keeps
     // the per-warp staging kernel
     for (int i = 0; i < lanes; ++i) {
@@ -400,14 +412,19 @@ int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* s
         launch_pyr_down0(st, ln.d_warped, c->pitch0(), c->padded_pixels(), c->d_mbasis, c->pitch0(), ln.d_fp, w, h, ln.d_mask0,
                          c->padded_pixels(), g_level(c, ln, 1), c->lv[1], nb);
     }
-    for (int k = 1; k < L; ++k) {
+    const int k0 = c->tail_k0;                  // levels k0 .. L: one launch
+    for (int k = 1; k < (k0 ? k0 : L); ++k) {
         Scope s(c, KC_PYR_DOWN, st);
         launch_pyr_down(st, g_level(c, ln, k), c->lv[k], g_level(c, ln, k + 1), c->lv[k + 1], nb);
     }
-    {   Scope s(c, KC_COLLAPSE, st);
+    if (k0) {
+        Scope s(c, KC_COLLAPSE, st);
+        launch_pyramid_tail(st, ln.d_g, ln.d_o, c->d_tail_levels, k0, L, nb);
+    } else {
+        Scope s(c, KC_COLLAPSE, st);
         launch_blend_coarsest(st, g_level(c, ln, L), c->lv[L], o_level(c, ln, L), nb);
     }
-    for (int k = L - 1; k >= 1; --k) {
+    for (int k = (k0 ? k0 : L) - 1; k >= 1; --k) {
         Scope s(c, KC_COLLAPSE, st);
         launch_collapse(st, g_level(c, ln, k), c->lv[k], g_level(c, ln, k + 1), o_level(c, ln, k + 1), c->lv[k + 1], o_level(c, ln, k), nb,
                         level_maps(ln, k));
@@ -548,6 +565,13 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
         c->o_floats += 3 * d.plane_stride;
         lw = (lw + 1) / 2; lh = (lh + 1) / 2;
     }
+    // the pyramid's tail: from the first level no larger than 32 x 32 on, all levels run in one launch
+    {
+        const char* e = std::getenv("POPPY_CUDA_TAIL");
+        if (!(e && e[0] == '0'))
+            for (int k = 1; k < pyramid_levels; ++k)
+                if (c->lv[k].w <= 32 && c->lv[k].h <= 32) { c->tail_k0 = k; break; }
+    }
     // triangle binning: 64x32 screen tiles; list capacity per frame (a frame that needs more falls back to testing
     // every triangle in every tile, see k_raster_warp)
     {
@@ -606,6 +630,7 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
         if (c->a_src[i]) cudaFreeArray(c->a_src[i]);
     }
     cudaFree(c->d_pts1_raw); cudaFree(c->d_pts2_raw); cudaFree(c->d_pts1); cudaFree(c->d_pts2); cudaFree(c->d_morphed);
+    cudaFree(c->d_tail_levels);
     cudaFree(c->d_frames); cudaFree(c->d_sum); cudaFree(c->d_calm_total); cudaFree(c->d_probe_total);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
