@@ -38,8 +38,8 @@ KEYS = [
 
 def short(name: str) -> str:
     name = re.sub(r"^void\s+", "", name)
-    name = re.sub(r"\(.*$", "", name)
-    return name.replace("poppy::", "")
+    name = re.sub(r"\((?!bool|int).*$", "", name)
+    return name.replace("poppy::", "").replace("(bool)", "").replace("(int)", "")
 
 
 def launches(path):
@@ -78,6 +78,7 @@ def full(path):
 
 
 CLASS_OF = [("k_raster_warp", "raster_warp"), ("k_pyr_down", "pyr_down"), ("k_collapse_roll", "blend_collapse"),
+            ("k_collapse_tma", "blend_collapse"), ("k_pyramid_tail", "blend_collapse"), ("k_calm", "calm_analysis"),
             ("k_blend_coarsest", "blend_collapse"), ("k_unsharp", "unsharp_store"), ("k_tri_geometry", "tri_geometry"),
             ("k_bin_", "bin_triangles"), ("k_lerp_points", "lerp_points")]
 
