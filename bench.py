@@ -165,6 +165,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def mirror_tile(img: np.ndarray, w: int, h: int) -> np.ndarray:
+    """img repeated with alternating mirror images (no seams) up to h x w."""
+    ih, iw = img.shape[:2]
+    row = np.concatenate([img, img[:, ::-1]], axis=1)
+    cell = np.concatenate([row, row[::-1]], axis=0)
+    reps = (-(-h // (2 * ih)), -(-w // (2 * iw))) + (1,) * (img.ndim - 2)
+    return np.ascontiguousarray(np.tile(cell, reps)[:h, :w])
+
+
 # ------------------------------------------------------------------------------------------------------------------
 class Job:
     """The workload of one rank: inputs, frame schedule, and the config dict both arms print."""
@@ -186,6 +195,7 @@ class Job:
             self.phases, self.masks = ratio.astype(np.float32), ratio
             self.hashes = g["hashes"]
             self.name = "config1-chain"
+            self.data = "reference demo images"
             self.desc = (f"images/square.png -> images/circle.png (reference front end), {self.W}x{self.H}, {len(self.pts1)} matcher "
                          f"points, {self.F} chained frames, {self.L}-level pyramid (BASELINE.json configs[0])")
             self.scaling = "weak"
@@ -195,6 +205,14 @@ class Job:
             self.W, self.H, self.L = wl["w"], wl["h"], wl["levels"]
             inp = synth.make_inputs(self.W, self.H, wl["n_points"], wl["jitter"], wl["seed"])
             self.bgr1, self.bgr2, self.gabor2, self.pts1, self.pts2 = inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2
+            content = "synthetic (band-limited noise, full 8-bit range)"
+            if args.content == "photo":
+                # secondary line: the same geometry over photographic content - the reference's own demo pair
+                # (tests/golden/full/c1.npz: images/square.png, images/circle.png after its front end) mirror-tiled to size
+                g = np.load(os.path.join(ROOT, "tests", "golden", "full", "c1.npz"))
+                self.bgr1, self.bgr2, self.gabor2 = (mirror_tile(g[k], self.W, self.H) for k in ("corrected1", "corrected2", "gabor2"))
+                content = "the reference's demo pair (config 1 fixture) mirror-tiled"
+            self.data = "synthetic" if args.content == "synthetic" else "reference demo images, tiled; synthetic points"
             if args.total_frames:
                 self.total = args.total_frames
                 self.scaling = "strong"
@@ -210,7 +228,9 @@ class Job:
             self.name = args.workload
             cfg = {"1080p": "the 1080p point of the metric", "4k": "BASELINE.json configs[3]", "8k": "BASELINE.json configs[4]"}[args.workload]
             self.desc = (f"synthetic {self.W}x{self.H} BGR pair, {wl['n_points']}+4 matched points, {self.L}-level pyramid, "
-                         f"{self.total} independent phases over {world} rank(s) ({cfg})")
+                         if args.content == "synthetic" else
+                         f"{self.W}x{self.H} BGR pair = {content}, {wl['n_points']}+4 synthetic matched points, {self.L}-level pyramid, ")
+            self.desc += f"{self.total} independent phases over {world} rank(s) ({cfg})"
             self.parallelism = f"phase-sharded x{world}, no collective"
         self.frame_bytes = self.W * self.H * 3
         # frames resident in the HBM ring at once: the whole shard where it fits (8K: 300-frame slices, 30 GB)
@@ -305,7 +325,7 @@ def reference_arm(args, rank, world):
     out = {
         "impl": "reference", "metric": "morphed frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times),
-        "higher_is_better": True, "scaling": job.scaling, "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic" if not job.chain else "reference demo images",
+        "higher_is_better": True, "scaling": job.scaling, "vs_baseline": None, "dtype": "u8/f32", "data": job.data,
         "config": job.config(),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -325,6 +345,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--mode", default="direct", choices=["direct", "chain"])
     ap.add_argument("--workload", default="4k", choices=["1080p", "4k", "8k"])
+    ap.add_argument("--content", default="synthetic", choices=["synthetic", "photo"],
+                    help="pixel content of the pair: the synthetic texture (headline) or the reference's demo pair tiled to size")
     ap.add_argument("--frames", type=int, default=0, help="frame phases per step and rank (weak scaling; default: workload's)")
     ap.add_argument("--total-frames", type=int, default=0, help="frame phases per step over ALL ranks (strong scaling)")
     ap.add_argument("--ring", type=int, default=0, help="frames resident in the HBM ring (default: the shard, 300 at 8K)")
@@ -549,7 +571,7 @@ def main():
         out = {
             "metric": "morphed frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": job.scaling,
-            "vs_baseline": None, "dtype": "u8/f32", "data": "reference demo images" if job.chain else "synthetic",
+            "vs_baseline": None, "dtype": "u8/f32", "data": job.data,
             "config": job.config(),
             "e2e": {"value": frames_all / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "breakdown": e2e_parts, "single_call": single_call,
