@@ -34,6 +34,11 @@ int poppy_host_morph_points(const float* pts1_xy, const float* pts2_xy, int n, d
  * (a point with x >= width or y >= height after clipping). */
 int poppy_host_triangulate(const float* pts_xy, int n, int width, int height, int32_t* tri_idx, int cap, int* n_tri);
 
+/* The same triangle list, for callers that walk through the frames of a sequence one call at a time (morph_images() once per
+ * frame, reference src/poppy.hpp:215): the point-location walks of the calling thread's previous call predict this call's
+ * (each predicted step is verified, so the result never depends on the prediction); ~1.6x faster between neighbouring frames. */
+int poppy_host_triangulate_next(const float* pts_xy, int n, int width, int height, int32_t* tri_idx, int cap, int* n_tri);
+
 /* shape/mask ratio of frame j of an n_frames segment, reference src/poppy.hpp:181-210 with phase < 0:
  * 0 for j == 0, 1/(N-j) afterwards, capped at 1. */
 double poppy_host_chain_ratio(int j, int n_frames);

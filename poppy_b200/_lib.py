@@ -38,6 +38,7 @@ def load():
         # host stages (include/poppy_host.h)
         "poppy_host_morph_points": (i32, [vp, vp, i32, C.c_double, i32, i32, vp]),
         "poppy_host_triangulate": (i32, [vp, i32, i32, i32, vp, i32, C.POINTER(i32)]),
+        "poppy_host_triangulate_next": (i32, [vp, i32, i32, i32, vp, i32, C.POINTER(i32)]),
         "poppy_host_chain_ratio": (C.c_double, [i32, i32]),
         "poppy_host_plan_create": (i32, [C.POINTER(vp), vp, vp, i32, i32, i32, i32, vp, i32, i32]),
         "poppy_host_plan_triangles": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]),
@@ -105,7 +106,7 @@ CUDA_ABI_SYMBOLS = [
     "poppy_cuda_download_async", "poppy_cuda_download_wait", "poppy_cuda_alloc_pinned", "poppy_cuda_free_pinned",
 ]
 HOST_ABI_SYMBOLS = [
-    "poppy_host_morph_points", "poppy_host_triangulate", "poppy_host_chain_ratio", "poppy_host_plan_create",
+    "poppy_host_morph_points", "poppy_host_triangulate", "poppy_host_triangulate_next", "poppy_host_chain_ratio", "poppy_host_plan_create",
     "poppy_host_plan_triangles", "poppy_host_plan_points", "poppy_host_plan_destroy", "poppy_morph_images",
     "poppy_host_last_error", "poppy_host_writer_create", "poppy_host_writer_create_io", "poppy_host_writer_submit",
     "poppy_host_writer_flush", "poppy_host_writer_destroy", "poppy_host_writer_destroy_cuda",

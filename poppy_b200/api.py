@@ -94,7 +94,7 @@ def morph_images(img1, img2, corrected1, corrected2, gabor2, src_points1, src_po
     if p1.shape != p2.shape:
         raise ValueError("point sets differ in size")          # assert at src/algo.cpp:51
     morphed = host.morph_points(p1, p2, shape_ratio, w, h)     # host copy, needed for the topology
-    tri = host.triangulate(morphed, w, h)
+    tri = host.triangulate(morphed, w, h, sequential=True)
     r = _renderer(w, h, len(p1), len(tri), 1)
     r.set_pair(np.ascontiguousarray(corrected1), np.ascontiguousarray(corrected2), np.ascontiguousarray(gabor2))
     r.set_points(p1, p2)

@@ -1,8 +1,12 @@
 #include "delaunay.hpp"
 
+#include <emmintrin.h>
+
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <unordered_map>
 
 namespace poppy {
@@ -209,7 +213,86 @@ struct WalkCand {
 };
 }  // namespace
 
-bool DelaunayMesh::walk_run(Walk& w) const {
+void DelaunayMesh::MoveLog::open(WalkTrace* trace) {
+    t = trace;
+    acc = 0;
+    pos = limit = 0;
+    if (!t) return;
+    pos = t->first[t->points];
+    const uint64_t capacity = (uint64_t)t->bits.size() * 64;
+    limit = (uint32_t)std::min<uint64_t>((uint64_t)pos + WalkTrace::kMaxSteps, capacity > 64 ? capacity - 64 : 0);
+    if (limit < pos) limit = pos;
+    acc = (pos & 63) ? __atomic_load_n(&t->bits[pos >> 6], __ATOMIC_RELAXED) & ((1ull << (pos & 63)) - 1) : 0;
+}
+
+void DelaunayMesh::MoveLog::close() {
+    if (!t) return;
+    if ((size_t)t->points + 1 >= t->first.size()) return;                 // more points than begin() was told: not recorded
+    if (pos & 63) __atomic_store_n(&t->bits[pos >> 6], acc & ((1ull << (pos & 63)) - 1), __ATOMIC_RELAXED);
+    t->first[t->points + 1] = pos;
+    ++t->points;
+}
+
+namespace {
+// Bit pattern of tri_area(p, q.opt[1], q.opt[0]) = (o1.x - p.x) * (o0.y - p.y) - (o1.y - p.y) * (o0.x - p.x), evaluated with
+// the same double operations in the same order as tri_area() (SSE2: both differences of a point in one instruction).
+// The predicate of the edge's other direction, tri_area(p, opt[0], opt[1]), is its exact negation (the products commute
+// and rounding is symmetric), i.e. the sign bit flipped.
+inline int64_t area_bits(const float* opt, __m128d P) {
+    const __m128 v = _mm_load_ps(opt);                                  // o0.x o0.y o1.x o1.y
+    const __m128d d0 = _mm_sub_pd(_mm_cvtps_pd(v), P);                  // o0 - p
+    const __m128d d1 = _mm_sub_pd(_mm_cvtps_pd(_mm_movehl_ps(v, v)), P);     // o1 - p
+    const __m128d m = _mm_mul_pd(d1, _mm_shuffle_pd(d0, d0, 1));        // d1.x * d0.y , d1.y * d0.x
+    const __m128d a = _mm_sub_sd(m, _mm_unpackhi_pd(m, m));
+    return _mm_cvtsi128_si64(_mm_castpd_si128(a));
+}
+}  // namespace
+
+void DelaunayMesh::walk_guided(Walk& w, const uint64_t* bits, uint32_t first, int count, MoveLog* log) const {
+    if (w.r_cur == 0 || count <= 0) return;
+    const Quad* __restrict__ q = q_.data();
+    const __m128d P = _mm_set_pd((double)w.p.y, (double)w.p.x);
+    int e = w.e, budget = w.budget, wrong = 0;
+    bool moved = false;
+    MoveLog lg;
+    if (log) lg = *log;
+    for (int j = 0; j < count && budget > 0; ++j) {
+        const uint32_t b = first + (uint32_t)j;
+        const int bit = (int)((__atomic_load_n(&bits[b >> 6], __ATOMIC_RELAXED) >> (b & 63)) & 1);
+        const Quad& qe = q[e >> 2];
+        const int on = qe.next[e & 3], dp = rot(qe.next[(e + 3) & 3], 3);
+        int nxt = bit ? dp : on;                // the only value the next step's loads wait for
+        // the two orientation predicates of the step, off that chain
+        const int64_t ion = area_bits(&q[on >> 2].opt[0].x, P) ^ (int64_t)((uint64_t)((on >> 1) & 1) << 63);
+        const int64_t idp = area_bits(&q[dp >> 2].opt[0].x, P) ^ (int64_t)((uint64_t)((dp >> 1) & 1) << 63);
+        // what walk_step / walk_run do here: general position (neither predicate zero), not inside (not both > 0),
+        // move = (a_on > 0). Integer operations on the bit patterns: a compare-and-branch on a_on > 0 would mispredict
+        // every other step and throw away the loads the next steps have already started.
+        const int g_on = ion > 0, g_dp = idp > 0;                        // x > 0 (no NaNs; -0.0 and +0.0 are not > 0)
+        const int z = (int)(((uint64_t)ion << 1) == 0) | (int)(((uint64_t)idp << 1) == 0);
+        if (__builtin_expect(z | (g_on & g_dp), 0)) break;               // degenerate or inside: the ordinary walk decides
+        if (__builtin_expect(g_on ^ bit, 0)) {
+            // wrong prediction (an edge flipped since the guide was recorded): take the real move; the paths usually
+            // rejoin a step or two later with the same number of moves, so the following bits still apply
+            asm volatile("" ::: "memory");      // keeps this a branch: as a conditional move it would tie nxt to the predicates
+            nxt = g_on ? dp : on;
+            ++wrong;
+        }
+        --budget;
+        lg.push(g_on);
+        e = nxt;
+        moved = true;
+        if (__builtin_expect(wrong > 8, 0)) break;                       // the guide no longer describes this walk
+    }
+    w.e = e;
+    w.budget = budget;
+    if (moved) w.r_cur = -1;
+    if (log) *log = lg;
+}
+
+bool DelaunayMesh::walk_run(Walk& w) const { return walk_run(w, nullptr); }
+
+bool DelaunayMesh::walk_run(Walk& w, MoveLog* log) const {
     if (w.r_cur == 0) return false;
     const Quad* __restrict__ q = q_.data();
     const double px = w.p.x, py = w.p.y;
@@ -218,6 +301,12 @@ bool DelaunayMesh::walk_run(Walk& w) const {
         const int on = qx.next[x & 3], dp = rot(qx.next[(x + 3) & 3], 3);
         const Quad& qo = q[on >> 2];
         const Quad& qd = q[dp >> 2];
+        // one level further: the records fill(on) / fill(dp) will read their coordinates from (the quads of onext and
+        // dprev of both successors) start their way from L2 now, a whole step before the loads that need them
+        __builtin_prefetch(&q[qo.next[on & 3] >> 2]);
+        __builtin_prefetch(&q[qo.next[(on + 3) & 3] >> 2]);
+        __builtin_prefetch(&q[qd.next[dp & 3] >> 2]);
+        __builtin_prefetch(&q[qd.next[(dp + 3) & 3] >> 2]);
         const int ko = (on >> 1) & 1, kd = (dp >> 1) & 1;
         c.e = x; c.on = on; c.dp = dp;
         c.on_bx = (double)qo.opt[ko ^ 1].x - px; c.on_by = (double)qo.opt[ko ^ 1].y - py;
@@ -242,6 +331,7 @@ bool DelaunayMesh::walk_run(Walk& w) const {
             w.e = cur->e; w.r_cur = -1; w.where = kInside;
             return true;
         }
+        if (log) log->push(a_on > 0);
         cur = &nxt[a_on > 0];      // right of onext (then not right of dprev): cross dprev, else onext
     }
 }
@@ -271,14 +361,26 @@ DelaunayMesh::Where DelaunayMesh::classify(const Walk& w, int& out_edge, int& ou
     return where;
 }
 
-int DelaunayMesh::insert(Point2f p) {
+int DelaunayMesh::insert(Point2f p) { return insert(p, nullptr, 0, nullptr); }
+
+int DelaunayMesh::insert(Point2f p, const WalkTrace* guide, int index, WalkTrace* record, int guide_points) {
     Walk w;
+    MoveLog log;
+    if (record) log.open(record);
+    MoveLog* lg = record ? &log : nullptr;
     if (begin_walk(p, w)) {
+        if (guide && index < (guide_points >= 0 ? guide_points : guide->points)) {
+            const uint32_t f0 = guide->first[index];
+            walk_guided(w, guide->bits.data(), f0, (int)(guide->first[index + 1] - f0), lg);
+        }
         // general-position stretches run in the dependence-cut loop; a degenerate predicate is decided by one generic
         // step, after which the fast loop resumes
-        while (!walk_run(w))
+        while (!walk_run(w, lg)) {
+            if (lg) lg->stop();
             if (!walk_step(w)) break;
+        }
     }
+    if (record) log.close();
     return finish_insert(w);
 }
 
@@ -437,20 +539,38 @@ void triangulate_points_batch(const std::vector<Point2f>* sets, int count, int w
 }
 
 bool triangulate_points(std::vector<Point2f> points, int width, int height, std::vector<int32_t>& tri_idx,
-                        std::string* error) {
+                        std::string* error, const WalkTrace* guide, WalkTrace* record, const WalkPace* pace) {
     tri_idx.clear();
+    // whatever happens, a follower waiting on this triangulation is released when it ends
+    struct Release {
+        std::atomic<int>* p;
+        ~Release() { if (p) p->store(INT_MAX, std::memory_order_release); }
+    } release{pace ? pace->publish : nullptr};
     clip_points(points, width, height);
     std::vector<Point2f> uniq;
     std::vector<int32_t> first;
     make_uniq(points, uniq, &first);
+    if (record) record->begin((int)uniq.size());
     DelaunayMesh mesh(width, height, (int)uniq.size());
     std::vector<int32_t> owner(4, -1);        // mesh vertex id -> index of its first occurrence in `points`
+    int guide_ready = (pace && pace->follow) ? 0 : -1;      // points of the guide known to be published (-1: all of guide->points)
     for (size_t i = 0; i < uniq.size(); ++i) {
-        const int v = mesh.insert(uniq[i]);
+        if (guide_ready >= 0 && guide_ready != INT_MAX && (int)i >= guide_ready) {
+            // stay behind the triangulation that records the guide: its point i must be published before ours is predicted
+            for (int spins = 0;; ++spins) {
+                guide_ready = pace->follow->load(std::memory_order_acquire);
+                if (guide_ready > (int)i) break;
+                if (spins < 256) _mm_pause(); else std::this_thread::yield();
+            }
+        }
+        const int avail = guide_ready == INT_MAX ? -1 : guide_ready;
+        const int v = mesh.insert(uniq[i], guide, (int)i, record, avail);
         if (v < 0) {
             if (error) *error = mesh.error();
+            if (record) record->points = 0;       // (not freed: a follower may still be reading what was published)
             return false;
         }
+        if (pace && pace->publish) pace->publish->store((int)i + 1, std::memory_order_release);
         if (v >= (int)owner.size()) owner.resize(v + 1, -1);
         if (owner[v] < 0) owner[v] = first[i];
     }
@@ -459,6 +579,16 @@ bool triangulate_points(std::vector<Point2f> points, int width, int height, std:
     tri_idx.resize(ids.size());
     for (size_t i = 0; i < ids.size(); ++i) tri_idx[i] = owner[ids[i]];
     return true;
+}
+
+bool triangulate_points_next(std::vector<Point2f> points, int width, int height, std::vector<int32_t>& tri_idx,
+                             std::string* error) {
+    thread_local WalkTrace traces[2];
+    thread_local int cur = 0;
+    const bool ok = triangulate_points(std::move(points), width, height, tri_idx, error, traces[cur].empty() ? nullptr : &traces[cur],
+                                       &traces[cur ^ 1]);
+    if (ok) cur ^= 1;
+    return ok;
 }
 
 }  // namespace poppy

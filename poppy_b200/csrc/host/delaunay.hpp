@@ -9,6 +9,8 @@
 // get_triangle_indices by an O(1) table that returns the same first-occurrence index.
 #pragma once
 
+#include <atomic>
+#include <climits>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -26,6 +28,38 @@ void clip_points(std::vector<Point2f>& pts, int cols, int rows);
 // `pts` of unique point i.
 void make_uniq(const std::vector<Point2f>& pts, std::vector<Point2f>& out, std::vector<int32_t>* first_index = nullptr);
 
+// The moves of the point-location walks of one triangulation, one bit per general-position step (0: the walk crossed to
+// onext, 1: to dprev), per inserted point. Consecutive frames of a sequence move every point by a fraction of a pixel, so
+// the walks of frame f are an almost perfect PREDICTION of the walks of frame f + 1: DelaunayMesh::insert follows the
+// recorded moves speculatively and only checks each step's two orientation predicates against them, which turns the
+// walk's chain of dependent loads and compares (load -> load -> convert -> multiply -> compare -> select, ~25 ns per step)
+// into one dependent load per step with the predicates off the critical path. A wrong prediction is detected at the step
+// where it happens and the ordinary walk takes over from that very state, so any trace - stale, foreign or garbage -
+// yields exactly the triangulation an unguided insertion yields.
+struct WalkTrace {
+    static constexpr int kMaxSteps = 4096;       // recorded moves per point (longer walks are simply not predicted further)
+    std::vector<uint32_t> first;                 // per point: index of its first bit; first[points] = total
+    std::vector<uint64_t> bits;
+    int points = 0;
+    // Sized once per triangulation and never reallocated while it is recorded (moves that do not fit are dropped), so that
+    // another thread may read the points already published (WalkPace) while the rest is still being written.
+    void begin(int expected_points) {
+        points = 0;
+        first.assign((size_t)expected_points + 2, 0);
+        bits.assign((size_t)expected_points * 6 + kMaxSteps / 64 + 2, 0);       // 384 moves per point on average
+    }
+    void clear() { first.clear(); bits.clear(); points = 0; }
+    bool empty() const { return points == 0; }
+};
+
+// Lets the triangulation of frame f + 1 run a few points behind the triangulation of frame f on another thread, predicted by
+// the very walks frame f is recording: `follow` is the number of points the guide has published (INT_MAX when it is
+// complete), `publish` is where this triangulation reports its own progress.
+struct WalkPace {
+    const std::atomic<int>* follow = nullptr;
+    std::atomic<int>* publish = nullptr;
+};
+
 class DelaunayMesh {
 public:
     // bounding rect [0,w) x [0,h), as Subdiv2D(Rect(0,0,w,h))
@@ -35,6 +69,9 @@ public:
     // Subdiv2D::insert. Returns the vertex id (>= 4 for real points) or -1 when the point is outside the rect
     // (where cv::Subdiv2D throws StsOutOfRange); error() then describes it.
     int insert(Point2f pt);
+    // the same with the walk predicted by point `index` of `guide` (nullable) and recorded as the next point of `record`
+    // (nullable); identical results whatever the guide holds
+    int insert(Point2f pt, const WalkTrace* guide, int index, WalkTrace* record, int guide_points = -1);
 
     enum Where { kError = -2, kOutside = -1, kInside = 0, kVertex = 1, kOnEdge = 2 };
     struct Walk {
@@ -60,6 +97,25 @@ public:
     // load -> load -> predicate. Identical decisions to walk_step (same double arithmetic, same order); stops at the
     // first degenerate predicate. Returns true when the walk ended (w.where set), false when walk_step must continue.
     bool walk_run(Walk& w) const;
+
+    // Appends the moves of one walk to a WalkTrace (register accumulator, flushed per 64 moves).
+    struct MoveLog {
+        WalkTrace* t = nullptr;
+        uint64_t acc = 0;
+        uint32_t pos = 0, limit = 0;
+        void open(WalkTrace* trace);
+        void push(int bit) {
+            if (pos >= limit) return;
+            acc |= (uint64_t)bit << (pos & 63);
+            if ((++pos & 63) == 0) { __atomic_store_n(&t->bits[(pos >> 6) - 1], acc, __ATOMIC_RELAXED); acc = 0; }
+        }
+        void stop() { limit = pos; }            // a degenerate step: what follows is not a prefix of general-position moves
+        void close();
+    };
+    bool walk_run(Walk& w, MoveLog* log) const;
+    // Follows up to `count` predicted moves (bits first .. first + count - 1 of `bits`), verifying each; stops in front of
+    // the first step whose predicates disagree with the prediction (or end the walk, or are degenerate).
+    void walk_guided(Walk& w, const uint64_t* bits, uint32_t first, int count, MoveLog* log) const;
 
     // Subdiv2D::getTriangleList order; each triangle as three vertex ids (all >= 4).
     void triangles(std::vector<int32_t>& vertex_ids) const;
@@ -111,8 +167,15 @@ private:
 // The host stage of morph_images for one frame (reference src/algo.cpp:205-213): clip, dedupe, triangulate, and
 // return triangle vertex indices into `points` (first exact-equal occurrence), in getTriangleList order.
 // Returns false (with `error`) where the reference would throw.
+// guide / record (nullable): the walk traces of a neighbouring frame to predict from, and where to record this frame's.
 bool triangulate_points(std::vector<Point2f> points, int width, int height, std::vector<int32_t>& tri_idx,
-                        std::string* error = nullptr);
+                        std::string* error = nullptr, const WalkTrace* guide = nullptr, WalkTrace* record = nullptr,
+                        const WalkPace* pace = nullptr);
+
+// triangulate_points for callers that triangulate the frames of a sequence one call at a time (the reference's own pattern:
+// morph_images() once per frame): each call is predicted by the calling thread's previous call and records for the next.
+bool triangulate_points_next(std::vector<Point2f> points, int width, int height, std::vector<int32_t>& tri_idx,
+                             std::string* error = nullptr);
 
 // The same for `count` independent point sets (the frames of a sequence) on one thread, with the point-location walks
 // of up to `ways` meshes interleaved (see DelaunayMesh::walk_step). ok[i] / errors[i] as triangulate_points.

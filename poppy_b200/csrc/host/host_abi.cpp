@@ -1,10 +1,12 @@
 // extern "C" layer of the host stages (include/poppy_host.h).
 #include <atomic>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -64,6 +66,21 @@ poppy::Image8 view8(const uint8_t* p, int w, int h, size_t step) {
 }
 }  // namespace
 
+// The walk trace of the last frame a sequence planner call triangulated: it predicts the first frame of the next call.
+namespace {
+std::mutex g_trace_mutex;
+poppy::WalkTrace g_carried_trace;
+void take_carried_trace(poppy::WalkTrace& out) {
+    std::lock_guard<std::mutex> lock(g_trace_mutex);
+    std::swap(out, g_carried_trace);
+    g_carried_trace.clear();
+}
+void put_carried_trace(poppy::WalkTrace& t) {
+    std::lock_guard<std::mutex> lock(g_trace_mutex);
+    std::swap(g_carried_trace, t);
+}
+}  // namespace
+
 extern "C" {
 
 const char* poppy_host_last_error(void) { return g_host_error.c_str(); }
@@ -83,6 +100,17 @@ int poppy_host_triangulate(const float* pts, int n, int w, int h, int32_t* tri_i
     std::vector<int32_t> tri;
     std::string err;
     if (!poppy::triangulate_points(to_points(pts, n), w, h, tri, &err)) return host_fail(POPPY_CUDA_ERR_INVALID, err);
+    *n_tri = (int)tri.size() / 3;
+    if (*n_tri > cap) return host_fail(POPPY_CUDA_ERR_CAPACITY, "triangle buffer too small");
+    if (tri_idx && !tri.empty()) std::memcpy(tri_idx, tri.data(), tri.size() * sizeof(int32_t));
+    return 0;
+}
+
+int poppy_host_triangulate_next(const float* pts, int n, int w, int h, int32_t* tri_idx, int cap, int* n_tri) {
+    if (!pts || !n_tri || n < 0) return host_fail(POPPY_CUDA_ERR_INVALID, "null argument");
+    std::vector<int32_t> tri;
+    std::string err;
+    if (!poppy::triangulate_points_next(to_points(pts, n), w, h, tri, &err)) return host_fail(POPPY_CUDA_ERR_INVALID, err);
     *n_tri = (int)tri.size() / 3;
     if (*n_tri > cap) return host_fail(POPPY_CUDA_ERR_CAPACITY, "triangle buffer too small");
     if (tri_idx && !tri.empty()) std::memcpy(tri_idx, tri.data(), tri.size() * sizeof(int32_t));
@@ -126,11 +154,38 @@ int poppy_host_plan_create(poppy_host_plan** out, const float* p1, const float* 
     // (pays where the quad-edge tables of several meshes fit the core's cache; see delaunay.hpp)
     const char* ways_env = std::getenv("POPPY_PLAN_WAYS");
     const int ways = ways_env ? std::max(1, std::min(8, std::atoi(ways_env))) : 1;
-    // ways == 1 (default): one frame at a time per worker, with the dependence-cut point-location loop
-    // (DelaunayMesh::walk_run); POPPY_PLAN_WAYS > 1 selects the interleaved multi-frame walks instead
+    // ways == 1 (default): worker t triangulates frames t, t + nt, t + 2 nt, ... Frame f is PREDICTED by frame f - 1
+    // (poppy::WalkTrace), which another worker is triangulating at the same time: frame f runs a few points behind it
+    // (poppy::WalkPace), so every frame but the first is guided by its immediate neighbour - the distance at which the
+    // prediction is nearly perfect - and all workers stay busy. Frame 0 is predicted by the last frame of the previous call
+    // (the previous slice of the same sequence, typically); a stale guide costs its own mispredictions, never the result.
+    const char* guide_env = std::getenv("POPPY_PLAN_GUIDE");            // A/B switch: 0 = unguided walks
+    const bool guided = !(guide_env && guide_env[0] == '0');
+    const int ring = 2 * nt + 1;
+    std::vector<poppy::WalkTrace> traces(guided ? ring : 0);
+    std::unique_ptr<std::atomic<int>[]> progress(new std::atomic<int>[n_frames + 1]);
+    for (int f = 0; f <= n_frames; ++f) progress[f].store(0, std::memory_order_relaxed);
+    poppy::WalkTrace carried;                                           // the previous call's last trace
+    if (guided) take_carried_trace(carried);
+    std::atomic<int> worker_id{0};
     auto work_single = [&] {
-        for (int f; (f = next.fetch_add(1)) < n_frames;) {
-            if (!poppy::triangulate_points(plan->points[f], w, h, tris[f], &errs[f])) {
+        const int t = worker_id.fetch_add(1);
+        for (int f = t; f < n_frames; f += nt) {
+            bool ok;
+            if (!guided) {
+                ok = poppy::triangulate_points(plan->points[f], w, h, tris[f], &errs[f]);
+                progress[f].store(INT_MAX, std::memory_order_release);
+            } else {
+                // the ring slot of frame f was last used by frame f - ring, which frame f - ring + 1 was reading
+                if (f - ring + 1 >= 0)
+                    while (progress[f - ring + 1].load(std::memory_order_acquire) != INT_MAX) std::this_thread::yield();
+                poppy::WalkPace pace;
+                pace.publish = &progress[f];
+                pace.follow = f > 0 ? &progress[f - 1] : nullptr;
+                const poppy::WalkTrace* guide = f > 0 ? &traces[(f - 1) % ring] : (carried.empty() ? nullptr : &carried);
+                ok = poppy::triangulate_points(plan->points[f], w, h, tris[f], &errs[f], guide, &traces[f % ring], &pace);
+            }
+            if (!ok) {
                 int expected = -1;
                 failed.compare_exchange_strong(expected, f);
             }
@@ -154,6 +209,7 @@ int poppy_host_plan_create(poppy_host_plan** out, const float* p1, const float* 
     for (int i = 1; i < nt; ++i) pool.emplace_back(work);
     work();
     for (auto& t : pool) t.join();
+    if (guided && ways == 1 && n_frames > 0) put_carried_trace(traces[(n_frames - 1) % ring]);
     if (failed.load() >= 0) {
         std::string msg = "frame " + std::to_string(failed.load()) + ": " + errs[failed.load()];
         delete plan;
@@ -202,7 +258,9 @@ int poppy_morph_images(poppy_cuda_ctx* ctx, const uint8_t* c1, size_t step1, con
     lerp_points(a, b, s, w, h, m);
     std::vector<int32_t> tri;
     std::string err;
-    if (!poppy::triangulate_points(m, w, h, tri, &err)) return host_fail(POPPY_CUDA_ERR_INVALID, err);
+    // the reference calls morph_images() once per frame of a sequence: the previous call's point-location walks predict this
+    // call's (poppy::WalkTrace; any guide gives the same triangulation)
+    if (!poppy::triangulate_points_next(m, w, h, tri, &err)) return host_fail(POPPY_CUDA_ERR_INVALID, err);
     const int32_t offs[2] = {0, (int32_t)(tri.size() / 3)};
     int rc;
     if ((rc = poppy_cuda_set_pair(ctx, c1, step1, c2, step2, gabor2, gstep)) != 0 ||

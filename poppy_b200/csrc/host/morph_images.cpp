@@ -79,7 +79,7 @@ double morph_images(const Image8& img1, const Image8& /*img2*/, const Image8& co
     if (n) poppy_host_morph_points(p1, p2, n, shapeRatio, w, h, mp);
     std::vector<int32_t> tri;
     std::string err;
-    if (!triangulate_points(morphedPoints, w, h, tri, &err)) throw MorphError("morph_images: " + err);
+    if (!triangulate_points_next(morphedPoints, w, h, tri, &err)) throw MorphError("morph_images: " + err);
     const int n_tri = (int)tri.size() / 3;
 
     std::lock_guard<std::mutex> lock(g_mu);

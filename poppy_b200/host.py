@@ -30,14 +30,17 @@ def morph_points(pts1, pts2, shape_ratio, width, height) -> np.ndarray:
     return out
 
 
-def triangulate(pts, width, height) -> np.ndarray:
+def triangulate(pts, width, height, sequential=False) -> np.ndarray:
     """Triangle vertex indices (T x 3) of the Delaunay mesh of `pts` in cv::Subdiv2D::getTriangleList order
-    (reference src/algo.cpp:205-213)."""
+    (reference src/algo.cpp:205-213). sequential: the caller walks through the frames of a sequence call by call; the
+    previous call's point-location walks then predict this call's (same result, faster)."""
     pts = np.ascontiguousarray(pts, np.float32)
     cap = 2 * pts.shape[0] + 16
     tri = np.empty((cap, 3), np.int32)
     nt = C.c_int(0)
-    _host_check(_lib.load().poppy_host_triangulate(_ptr(pts), pts.shape[0], width, height, _ptr(tri), cap, C.byref(nt)))
+    lib = _lib.load()
+    fn = lib.poppy_host_triangulate_next if sequential else lib.poppy_host_triangulate
+    _host_check(fn(_ptr(pts), pts.shape[0], width, height, _ptr(tri), cap, C.byref(nt)))
     return tri[: nt.value].copy()
 
 

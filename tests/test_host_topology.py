@@ -111,3 +111,86 @@ def test_triangulation_matches_reference_at_scale(native_lib, kind):
     p = p.astype(np.float32)
     a, b = ref.triangulate(w, h, p), host.triangulate(p, w, h)
     assert a.shape == b.shape and (a == b).all(), kind
+
+
+def _points(kind, rng, w, h, n):
+    if kind == "uniform":
+        p = np.stack([rng.uniform(2, w - 3, n), rng.uniform(2, h - 3, n)], 1)
+    elif kind == "lattice":        # collinear runs, points on edges, duplicates: the degenerate predicates
+        p = np.stack([rng.integers(0, w // 20, n) * 20, rng.integers(0, h // 20, n) * 20], 1)
+    else:
+        c = rng.uniform(0.1 * w, 0.9 * w, (12, 2)) * [1, h / w]
+        p = np.clip(c[rng.integers(0, 12, n)] + rng.normal(0, 25, (n, 2)), 0, [w - 1, h - 1])
+    return p.astype(np.float32)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lattice", "clustered"])
+@pytest.mark.parametrize("jitter", [0.02, 1.5, 40.0])
+def test_guided_walks_give_the_unguided_triangulation(native_lib, kind, jitter):
+    """The sequence planner predicts each frame's point-location walks from the previous frame's (poppy::WalkTrace,
+    DelaunayMesh::walk_guided): whatever the guide holds - a neighbouring frame, a frame whose points moved far, the
+    previous CALL's unrelated point set - every frame's triangle list must be the one an unguided insertion gives."""
+    rng = np.random.default_rng(7)
+    w, h, n = 1280, 720, 3000
+    p1 = _points(kind, rng, w, h, n)
+    p2 = np.clip(p1 + rng.uniform(-jitter, jitter, p1.shape), 0, [w - 1, h - 1]).astype(np.float32)
+    phases = np.linspace(0, 1, 7).astype(np.float32)
+    # one thread: frames 1.. are guided by their predecessor; the first frame by what the previous test case left in the pool
+    plan = host.SequencePlan(p1, p2, w, h, phases, chain=False, threads=1)
+    for f, s in enumerate(phases):
+        mp = host.morph_points(p1, p2, float(s), w, h)
+        want = host.triangulate(mp, w, h)
+        got = plan.triangles(f)
+        assert got.shape == want.shape and (got == want).all(), (kind, jitter, f)
+    plan.close()
+    # a stale guide of a different size: a second, smaller, unrelated sequence planned right after
+    q1 = _points("uniform", rng, w, h, 700)
+    plan = host.SequencePlan(q1, q1[::-1].copy(), w, h, phases[:3], chain=False, threads=1)
+    for f, s in enumerate(phases[:3]):
+        mp = host.morph_points(q1, q1[::-1].copy(), float(s), w, h)
+        assert (plan.triangles(f) == host.triangulate(mp, w, h)).all(), (kind, jitter, f, "stale guide")
+    plan.close()
+
+
+@pytest.mark.parametrize("threads", [2, 5, 16])
+def test_paced_planner_threads_follow_each_other(native_lib, threads):
+    """With several workers frame f is triangulated a few points behind frame f - 1 on another thread and predicted by the
+    trace that thread is still recording (poppy::WalkPace). Repeated to give a race a chance to show."""
+    rng = np.random.default_rng(threads)
+    w, h, n = 960, 540, 1500
+    for rep in range(3):
+        p1 = _points(["uniform", "lattice", "clustered"][rep], rng, w, h, n)
+        p2 = np.clip(p1 + rng.uniform(-3, 3, p1.shape), 0, [w - 1, h - 1]).astype(np.float32)
+        phases = np.linspace(0, 1, 37).astype(np.float32)
+        plan = host.SequencePlan(p1, p2, w, h, phases, chain=False, threads=threads)
+        for f in range(0, 37, 3):
+            mp = host.morph_points(p1, p2, float(phases[f]), w, h)
+            want = host.triangulate(mp, w, h)
+            assert plan.triangles(f).shape == want.shape and (plan.triangles(f) == want).all(), (threads, rep, f)
+        plan.close()
+
+
+def test_sequential_triangulate_matches_plain(native_lib):
+    rng = np.random.default_rng(5)
+    w, h = 800, 600
+    p1 = _points("uniform", rng, w, h, 900)
+    p2 = np.clip(p1 + rng.uniform(-5, 5, p1.shape), 0, [w - 1, h - 1]).astype(np.float32)
+    for s in np.linspace(0, 1, 6):
+        mp = host.morph_points(p1, p2, float(s), w, h)
+        assert (host.triangulate(mp, w, h, sequential=True) == host.triangulate(mp, w, h)).all()
+    other = _points("lattice", rng, w, h, 400)           # an unrelated point set right after: stale guide
+    assert (host.triangulate(other, w, h, sequential=True) == host.triangulate(other, w, h)).all()
+
+
+@pytest.mark.skipif(not ref.available(), reason="reference library not built")
+def test_guided_planner_matches_reference_subdiv2d(native_lib):
+    rng = np.random.default_rng(11)
+    w, h, n = 1920, 1080, 5000
+    p1 = _points("uniform", rng, w, h, n)
+    p2 = np.clip(p1 + rng.uniform(-6, 6, p1.shape), 0, [w - 1, h - 1]).astype(np.float32)
+    phases = np.linspace(0.3, 0.32, 5).astype(np.float32)
+    plan = host.SequencePlan(p1, p2, w, h, phases, chain=False, threads=1)
+    for f, s in enumerate(phases):
+        mp = host.morph_points(p1, p2, float(s), w, h)
+        a = ref.triangulate(w, h, mp)
+        assert a.shape == plan.triangles(f).shape and (a == plan.triangles(f)).all(), f
