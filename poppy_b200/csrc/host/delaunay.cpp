@@ -32,13 +32,22 @@ uint64_t point_key(Point2f p) {
 }  // namespace
 
 void make_uniq(const std::vector<Point2f>& pts, std::vector<Point2f>& out, std::vector<int32_t>* first_index) {
-    std::unordered_map<uint64_t, int> seen;
-    seen.reserve(pts.size() * 2);
+    // open-addressing set of the bit patterns seen so far (slot = index + 1 of the first occurrence, 0 = empty)
+    size_t cap = 16;
+    while (cap < pts.size() * 2 + 2) cap <<= 1;
+    std::vector<int32_t> slot(cap, 0);
+    out.reserve(out.size() + pts.size());
+    if (first_index) first_index->reserve(first_index->size() + pts.size());
     for (size_t i = 0; i < pts.size(); ++i) {
-        if (seen.emplace(point_key(pts[i]), (int)i).second) {
-            out.push_back(pts[i]);
-            if (first_index) first_index->push_back((int32_t)i);
-        }
+        const uint64_t key = point_key(pts[i]);
+        size_t h = (size_t)((key * 0x9E3779B97F4A7C15ull) >> 17) & (cap - 1);
+        bool seen = false;
+        for (; slot[h]; h = (h + 1) & (cap - 1))
+            if (point_key(pts[slot[h] - 1]) == key) { seen = true; break; }
+        if (seen) continue;
+        slot[h] = (int32_t)i + 1;
+        out.push_back(pts[i]);
+        if (first_index) first_index->push_back((int32_t)i);
     }
 }
 
@@ -407,13 +416,22 @@ int DelaunayMesh::finish_insert(Walk& w) {
     } while (dst(cur) != first);
     cur = oprev(base);
     const int budget = (int)q_.size() * 4;
+    // The swap loop reads every coordinate from the quad records it is walking anyway (Quad::opt mirrors pt_[org]); the
+    // vertex tables (org_ -> pt_, two more dependent loads per point) are not touched. Vertices of a mesh have pairwise
+    // different coordinates (insert() returns the existing vertex for a repeated point), so "org(cur) == first" can be
+    // decided on the coordinates as well.
+    const Point2f first_pt = pt_[first];
     for (int i = 0; i < budget; ++i) {
         const int t = oprev(cur);
-        const int t_dst = dst(t), c_org = org(cur), c_dst = dst(cur);
-        if (side_of(pt_[t_dst], cur) > 0 && in_circle(pt_[c_org], pt_[t_dst], pt_[c_dst], pt_[v]) < 0) {
+        const Quad& qc = q_[cur >> 2];
+        const Quad& qt = q_[t >> 2];
+        const int kc = (cur >> 1) & 1, kt = (t >> 1) & 1;
+        const Point2f c_org = qc.opt[kc], c_dst = qc.opt[kc ^ 1], t_dst = qt.opt[kt ^ 1];
+        const double cw = tri_area(t_dst, c_dst, c_org);                 // side_of(t_dst, cur)
+        if (cw > 0 && in_circle(c_org, t_dst, c_dst, p) < 0) {
             flip(cur);
             cur = oprev(cur);
-        } else if (c_org == first) {
+        } else if (c_org.x == first_pt.x && c_org.y == first_pt.y) {
             break;
         } else {
             cur = lprev(onext(cur));
