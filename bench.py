@@ -483,7 +483,7 @@ def main():
         def planner():
             for a, b in slices:
                 t0 = time.perf_counter()
-                p = host.SequencePlan(job.pts1, job.pts2, W, H, phases[a:b], chain=job.chain, threads=plan_threads)
+                p = host.SequencePlan(job.pts1, job.pts2, W, H, phases[a:b], chain=job.chain, threads=plan_threads, copy=False)
                 plan_busy[0] += time.perf_counter() - t0
                 plans.put((a, b, p))
 

@@ -52,7 +52,9 @@ def chain_ratio(j, n_frames) -> float:
 class SequencePlan:
     """Morphed points + triangle lists of every frame of a sequence, planned on host threads."""
 
-    def __init__(self, pts1, pts2, width, height, shape_ratio, chain=False, threads=0):
+    def __init__(self, pts1, pts2, width, height, shape_ratio, chain=False, threads=0, copy=True):
+        """copy=False: tri_idx / tri_offsets are views of the plan's own memory, valid until close() (a 600-frame plan at 4K
+        holds 290 MB of triangle indices; the streaming callers hand them to the renderer and close the plan right after)."""
         self._lib = _lib.load()
         pts1 = np.ascontiguousarray(pts1, np.float32)
         pts2 = np.ascontiguousarray(pts2, np.float32)
@@ -67,8 +69,11 @@ class SequencePlan:
         self.max_triangles = mx.value
         self.tri_offsets = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_int32)), shape=(self.frames + 1,)).copy()
         total = int(self.tri_offsets[-1])
-        self.tri_idx = (np.ctypeslib.as_array(C.cast(tri, C.POINTER(C.c_int32)), shape=(total * 3,)).copy().reshape(-1, 3)
-                        if total else np.zeros((0, 3), np.int32))
+        if total:
+            view = np.ctypeslib.as_array(C.cast(tri, C.POINTER(C.c_int32)), shape=(total * 3,))
+            self.tri_idx = (view.copy() if copy else view).reshape(-1, 3)
+        else:
+            self.tri_idx = np.zeros((0, 3), np.int32)
 
     def points(self, frame) -> np.ndarray:
         p = C.c_void_p()
