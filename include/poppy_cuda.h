@@ -170,6 +170,15 @@ const char* poppy_cuda_last_error(const poppy_cuda_ctx* ctx);
 /* Build identification: "poppy_cuda <version> sm_100a". */
 const char* poppy_cuda_version(void);
 
+/* ---- input conditioning ahead of the path ----------------------------------------------------------
+ * poppy::blur_margin(src, szUnion, dst), reference src/util.cpp:574-602: the 8-bit BGR source centred on a black
+ * union_w x union_h canvas whose four margins are blurred by cv::GaussianBlur(127 x 127, sigma 6) (OpenCV's fixed-point
+ * 8-bit path, reproduced exactly). Stand-alone (no context): runs on `device`, fails with POPPY_CUDA_ERR_NO_DEVICE without
+ * one and with POPPY_CUDA_ERR_INVALID where the reference's cv::Mat ROI assertions would throw. */
+int poppy_cuda_blur_margin(int device, const uint8_t* src, size_t src_step, int cols, int rows, int union_w, int union_h,
+                           uint8_t* dst, size_t dst_step);
+const char* poppy_cuda_blur_margin_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

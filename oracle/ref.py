@@ -230,3 +230,21 @@ def mask(gabor2, mask_ratio):
     out = np.empty((h, w), np.float32)
     _check(lib().poppy_ref_mask(_p(gabor2), w, h, C.c_double(mask_ratio), _p(out)))
     return out
+
+
+def blur_margin(src, union_size):
+    """poppy::blur_margin (reference src/util.cpp:574-602); union_size = (width, height)."""
+    src = _u8(src)
+    h, w = src.shape[:2]
+    uw, uh = int(union_size[0]), int(union_size[1])
+    out = np.empty((uh, uw, 3), np.uint8)
+    _check(lib().poppy_ref_blur_margin(_p(src), w, h, uw, uh, _p(out)))
+    return out
+
+
+def gaussian_blur_u8(src, ksize, sigma):
+    src = _u8(src)
+    h, w = src.shape[:2]
+    out = np.empty_like(src)
+    _check(lib().poppy_ref_gaussian_blur_u8(_p(src), w, h, int(ksize), C.c_double(sigma), _p(out)))
+    return out

@@ -303,4 +303,25 @@ int poppy_ref_synth_image(int w, int h, uint64_t seed, double sigma, uint8_t* ou
     });
 }
 
+// input conditioning ahead of the path: poppy::blur_margin (src/util.cpp:574-602) and the 8-bit
+// GaussianBlur it is made of (OpenCV's fixed-point path)
+int poppy_ref_blur_margin(const uint8_t* src, int w, int h, int union_w, int union_h, uint8_t* out) {
+    return guarded([&] {
+        cv::Mat s(h, w, CV_8UC3, const_cast<uint8_t*>(src));
+        cv::Mat dst;
+        poppy::blur_margin(s, cv::Size(union_w, union_h), dst);
+        if (dst.cols != union_w || dst.rows != union_h || dst.type() != CV_8UC3) throw std::runtime_error("blur_margin: unexpected result");
+        for (int y = 0; y < union_h; ++y) std::memcpy(out + (size_t)y * union_w * 3, dst.ptr(y), (size_t)union_w * 3);
+    });
+}
+
+int poppy_ref_gaussian_blur_u8(const uint8_t* src, int w, int h, int ksize, double sigma, uint8_t* out) {
+    return guarded([&] {
+        cv::Mat s(h, w, CV_8UC3, const_cast<uint8_t*>(src));
+        cv::Mat dst;
+        cv::GaussianBlur(s.clone(), dst, cv::Size(ksize, ksize), sigma);
+        for (int y = 0; y < h; ++y) std::memcpy(out + (size_t)y * w * 3, dst.ptr(y), (size_t)w * 3);
+    });
+}
+
 }  // extern "C"

@@ -103,6 +103,24 @@ def morph_images(img1, img2, corrected1, corrected2, gabor2, src_points1, src_po
     return dst, r.morphed_points(0)
 
 
+def blur_margin(src, union_size):
+    """poppy::blur_margin (reference src/util.cpp:574-602) on the GPU: `src` (H x W x 3 uint8) centred on a black canvas of
+    union_size = (width, height) with its four margins Gaussian-blurred. Returns the canvas."""
+    from . import _lib
+    import ctypes as C
+    src = np.ascontiguousarray(src, np.uint8)
+    if src.ndim != 3 or src.shape[2] != 3:
+        raise ValueError("blur_margin: expected an H x W x 3 uint8 image")
+    uw, uh = int(union_size[0]), int(union_size[1])
+    dst = np.empty((max(uh, 0), max(uw, 0), 3), np.uint8)
+    lib = _lib.load()
+    rc = lib.poppy_cuda_blur_margin(Settings.instance().cuda_device, src.ctypes.data_as(C.c_void_p), src.strides[0], src.shape[1],
+                                    src.shape[0], uw, uh, dst.ctypes.data_as(C.c_void_p), dst.strides[0] if dst.size else 0)
+    if rc != 0:
+        raise RuntimeError(f"poppy_cuda_blur_margin failed ({rc}): {lib.poppy_cuda_blur_margin_last_error().decode()}")
+    return dst
+
+
 def morph_sequence(corrected1, corrected2, gabor2, src_points1, src_points2, writer=None, number_of_frames=None,
                    threads=0):
     """Chain mode: frame j = morph_images(previous frame, previous morphed points, shape = color = 1/(N-j)).

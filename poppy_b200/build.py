@@ -18,6 +18,7 @@ CUDA_SOURCES = [
     "device/kernels_warp.cu",
     "device/kernels_pyramid.cu",
     "device/kernels_unsharp.cu",
+    "margin.cu",
 ]
 HOST_SOURCES = [
     "host/delaunay.cpp",
