@@ -177,7 +177,15 @@ const char* poppy_cuda_version(void);
  * one and with POPPY_CUDA_ERR_INVALID where the reference's cv::Mat ROI assertions would throw. */
 int poppy_cuda_blur_margin(int device, const uint8_t* src, size_t src_step, int cols, int rows, int union_w, int union_h,
                            uint8_t* dst, size_t dst_step);
-const char* poppy_cuda_blur_margin_last_error(void);
+const char* poppy_cuda_blur_margin_last_error(void);      /* of the calling thread's last blur_margin / gabor_filter call */
+
+/* poppy::gabor_filter(src, dst) with the reference's defaults (src/util.cpp:40-60, src/util.hpp:95, called at
+ * src/poppy.hpp:122): src / dst are float BGR (rows x cols x 3), dst = mean over 16 orientations of the clamped 13 x 13 Gabor
+ * responses. cv::filter2D evaluates these by a double-precision block DFT; this entry point sums the same correlation directly
+ * in double, so results agree to the float rounding of a value known to ~1e-15: floating-point parity with tolerance
+ * (|diff| <= 1.2e-7 everywhere; on textured images at most 20 values per million differ by more than the DFT's own round-off
+ * around zero, 1e-12; tests/test_margin.py), not bit-exact. */
+int poppy_cuda_gabor_filter(int device, const float* src, size_t src_step, int cols, int rows, float* dst, size_t dst_step);
 
 #ifdef __cplusplus
 }

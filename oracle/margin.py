@@ -97,3 +97,51 @@ def blur_margin(src: np.ndarray, union_size) -> np.ndarray:
     for x, y, w, h in margins:
         out[y:y + h, x:x + w] = gaussian_blur_u8(canvas[y:y + h, x:x + w], 127, 6.0)
     return out
+
+
+# ---- gabor_filter (reference src/util.cpp:40-60, called with its defaults at src/poppy.hpp:122) ------------------------------
+# dst = (1/16) * sum_i clamp01(filter2D(src, getGaborKernel(13 x 13, sigma 5, theta_i, lambda 10, gamma 0.04, psi pi/4)))
+# with theta_i = i * float(180 / 16) = 11 i (degrees handed to a function that takes radians - reproduced as is).
+# cv::filter2D routes a 13 x 13 float kernel over a float image through crossCorr (OCV imgproc/src/filter.dispatch.cpp:1291:
+# kernel area 169 >= 130), which promotes 32-bit float images to DOUBLE (templmatch.cpp:592 maxDepth), correlates block-wise by
+# DFT and rounds the result back to float. This restatement evaluates the same correlation directly in double
+# (BORDER_REFLECT_101, anchor at the centre): it agrees with the DFT evaluation to ~1e-15 relative, i.e. the float results are
+# equal except where the exact value lies within that distance of a float rounding boundary (a few values per hundred
+# million, off by one float ulp). FLOATING-POINT PARITY WITH TOLERANCE, stated in tests/test_margin.py - not bit-exact.
+GABOR = dict(angles=16, ksize=13, sigma=5.0, lambd=10.0, gamma=0.04, psi=math.pi / 4)
+
+
+def gabor_kernel(ksize: int, sigma: float, theta: float, lambd: float, gamma: float, psi: float) -> np.ndarray:
+    """cv::getGaborKernel(..., CV_32F) (OCV imgproc/src/gabor.cpp:51-95)."""
+    sigma_x, sigma_y = sigma, sigma / gamma
+    c, s = math.cos(theta), math.sin(theta)
+    xmax = ymax = ksize // 2
+    ex, ey = -0.5 / (sigma_x * sigma_x), -0.5 / (sigma_y * sigma_y)
+    cscale = math.pi * 2 / lambd
+    k = np.empty((2 * ymax + 1, 2 * xmax + 1), np.float32)
+    for y in range(-ymax, ymax + 1):
+        for x in range(-xmax, xmax + 1):
+            xr = x * c + y * s
+            yr = -x * s + y * c
+            k[ymax - y, xmax - x] = np.float32(1.0 * math.exp(ex * xr * xr + ey * yr * yr) * math.cos(cscale * xr + psi))
+    return k
+
+
+def gabor_thetas() -> list[float]:
+    step = float(np.float32(180 // GABOR["angles"]))          # float step = (180 / numAngles): integer division
+    return [i * step for i in range(GABOR["angles"])]
+
+
+def gabor_filter(src: np.ndarray) -> np.ndarray:
+    from scipy.ndimage import correlate
+    src = np.ascontiguousarray(src, np.float32)
+    dst = np.zeros_like(src)
+    for theta in gabor_thetas():
+        k = gabor_kernel(GABOR["ksize"], GABOR["sigma"], theta, GABOR["lambd"], GABOR["gamma"], GABOR["psi"]).astype(np.float64)
+        plane = np.empty_like(src)
+        for c in range(src.shape[2]):
+            plane[..., c] = correlate(src[..., c].astype(np.float64), k, mode="mirror").astype(np.float32)
+        plane[plane > 1.0] = 1.0
+        plane[plane < 0.0] = 0.0
+        dst += plane
+    return dst / np.float32(GABOR["angles"])

@@ -248,3 +248,19 @@ def gaussian_blur_u8(src, ksize, sigma):
     out = np.empty_like(src)
     _check(lib().poppy_ref_gaussian_blur_u8(_p(src), w, h, int(ksize), C.c_double(sigma), _p(out)))
     return out
+
+
+def gabor_filter(src):
+    """poppy::gabor_filter(src, dst) with the reference's defaults (src/util.cpp:40-60, called at src/poppy.hpp:122)."""
+    src = _f32(src)
+    h, w = src.shape[:2]
+    out = np.empty_like(src)
+    _check(lib().poppy_ref_gabor_filter(_p(src), w, h, _p(out)))
+    return out
+
+
+def gabor_kernel(ksize, sigma, theta, lambd, gamma, psi):
+    out = np.empty((ksize, ksize), np.float32)
+    _check(lib().poppy_ref_gabor_kernel(int(ksize), C.c_double(sigma), C.c_double(theta), C.c_double(lambd), C.c_double(gamma),
+                                        C.c_double(psi), _p(out)))
+    return out

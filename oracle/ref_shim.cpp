@@ -315,6 +315,23 @@ int poppy_ref_blur_margin(const uint8_t* src, int w, int h, int union_w, int uni
     });
 }
 
+// poppy::gabor_filter with its defaults, as src/poppy.hpp:122 calls it (16 angles, 13 x 13, sigma 5, lambda 10, gamma 0.04, psi pi/4)
+int poppy_ref_gabor_filter(const float* src, int w, int h, float* out) {
+    return guarded([&] {
+        cv::Mat dst;
+        poppy::gabor_filter(wrap_f32(src, w, h, 3), dst);
+        copy_out(dst, out);
+    });
+}
+
+// cv::getGaborKernel as gabor_filter requests it (CV_32F), row-major ksize x ksize
+int poppy_ref_gabor_kernel(int ksize, double sigma, double theta, double lambd, double gamma, double psi, float* out) {
+    return guarded([&] {
+        cv::Mat k = cv::getGaborKernel(cv::Size(ksize, ksize), sigma, theta, lambd, gamma, psi, CV_32F);
+        copy_out(k, out);
+    });
+}
+
 int poppy_ref_gaussian_blur_u8(const uint8_t* src, int w, int h, int ksize, double sigma, uint8_t* out) {
     return guarded([&] {
         cv::Mat s(h, w, CV_8UC3, const_cast<uint8_t*>(src));

@@ -75,6 +75,7 @@ def load():
         "poppy_cuda_free_pinned": (None, [vp]),
         "poppy_cuda_blur_margin": (i32, [i32, vp, C.c_size_t, i32, i32, i32, i32, vp, C.c_size_t]),
         "poppy_cuda_blur_margin_last_error": (C.c_char_p, []),
+        "poppy_cuda_gabor_filter": (i32, [i32, vp, C.c_size_t, i32, i32, vp, C.c_size_t]),
         "poppy_cuda_get_morphed_points": (i32, [vp, i32, vp]),
         "poppy_cuda_frame_device_ptr": (i32, [vp, i32, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "poppy_cuda_checksum": (i32, [vp, i32, i32, u64p]),
@@ -106,7 +107,7 @@ CUDA_ABI_SYMBOLS = [
     "poppy_cuda_version", "poppy_cuda_get_info", "poppy_cuda_set_tile_list_capacity", "poppy_cuda_set_unsharp_mode",
     "poppy_cuda_unsharp_stats", "poppy_cuda_set_image", "poppy_cuda_set_source1_from_slot",
     "poppy_cuda_download_async", "poppy_cuda_download_wait", "poppy_cuda_alloc_pinned", "poppy_cuda_free_pinned",
-    "poppy_cuda_blur_margin", "poppy_cuda_blur_margin_last_error",
+    "poppy_cuda_blur_margin", "poppy_cuda_blur_margin_last_error", "poppy_cuda_gabor_filter",
 ]
 HOST_ABI_SYMBOLS = [
     "poppy_host_morph_points", "poppy_host_triangulate", "poppy_host_triangulate_next", "poppy_host_chain_ratio", "poppy_host_plan_create",

@@ -121,6 +121,23 @@ def blur_margin(src, union_size):
     return dst
 
 
+def gabor_filter(src):
+    """poppy::gabor_filter(src, dst) with the reference's defaults (src/util.cpp:40-60) on the GPU; src: H x W x 3 float32
+    (the reference passes corrected2 / 255). Agrees with the reference to float rounding (see include/poppy_cuda.h)."""
+    from . import _lib
+    import ctypes as C
+    src = np.ascontiguousarray(src, np.float32)
+    if src.ndim != 3 or src.shape[2] != 3:
+        raise ValueError("gabor_filter: expected an H x W x 3 float32 image")
+    dst = np.empty_like(src)
+    lib = _lib.load()
+    rc = lib.poppy_cuda_gabor_filter(Settings.instance().cuda_device, src.ctypes.data_as(C.c_void_p), src.strides[0], src.shape[1],
+                                     src.shape[0], dst.ctypes.data_as(C.c_void_p), dst.strides[0])
+    if rc != 0:
+        raise RuntimeError(f"poppy_cuda_gabor_filter failed ({rc}): {lib.poppy_cuda_blur_margin_last_error().decode()}")
+    return dst
+
+
 def morph_sequence(corrected1, corrected2, gabor2, src_points1, src_points2, writer=None, number_of_frames=None,
                    threads=0):
     """Chain mode: frame j = morph_images(previous frame, previous morphed points, shape = color = 1/(N-j)).

@@ -90,6 +90,65 @@ __global__ void k_margin_cols(const uint16_t* __restrict__ tmp, int x0, int y0, 
     out[(size_t)(y0 + y) * pitch + (size_t)x0 * 3 + i] = (uint8_t)(v > 255u ? 255u : v);
 }
 
+// ---- gabor_filter (reference src/util.cpp:40-60, defaults as src/poppy.hpp:122 calls it) ----------------------------------------
+// dst = (1/16) sum_i clamp01(filter2D(src, gaborKernel_i)); cv::filter2D sends a 13 x 13 float kernel over a float image
+// through crossCorr, which promotes to DOUBLE, correlates by block DFT and rounds back to float (filter.dispatch.cpp:1291,
+// templmatch.cpp:592). Here the same correlation is summed directly in double (BORDER_REFLECT_101, centre anchor): equal
+// to the DFT evaluation to ~1e-15, so the float results differ only where the exact value sits on a float rounding
+// boundary (measured: 0-1 values per million, by one ulp). Floating-point parity with a stated tolerance, not bit-exact.
+constexpr int GB_ANGLES = 16, GB_K = 13, GB_R = GB_K / 2, GB_TW = 32, GB_TH = 4;
+__constant__ double c_gabor_taps[GB_ANGLES * GB_K * GB_K];
+
+// block (96, 4): thread = (pixel x within the 32-pixel tile, channel) x row; grid (ceil(w / 32), ceil(h / 4))
+__global__ void __launch_bounds__(3 * GB_TW * GB_TH)
+k_gabor(const float* __restrict__ src, size_t spitch, int w, int h, float* __restrict__ dst, size_t dpitch) {
+    __shared__ float tile[GB_TH + 2 * GB_R][(GB_TW + 2 * GB_R) * 3];
+    const int bx = blockIdx.x * GB_TW, by = blockIdx.y * GB_TH;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    constexpr int TW3 = (GB_TW + 2 * GB_R) * 3;
+    for (int i = tid; i < (GB_TH + 2 * GB_R) * TW3; i += 3 * GB_TW * GB_TH) {
+        const int ty = i / TW3, tx = i - ty * TW3, px = tx / 3, c = tx - 3 * px;
+        const int gx = margin_reflect(bx + px - GB_R, w), gy = margin_reflect(by + ty - GB_R, h);
+        tile[ty][tx] = src[(size_t)gy * spitch + (size_t)gx * 3 + c];
+    }
+    __syncthreads();
+    const int px = threadIdx.x / 3, c = threadIdx.x - 3 * px, gx = bx + px, gy = by + threadIdx.y;
+    if (gx >= w || gy >= h) return;
+    double acc[GB_ANGLES];
+#pragma unroll
+    for (int a = 0; a < GB_ANGLES; ++a) acc[a] = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < GB_K; ++i) {
+#pragma unroll
+        for (int j = 0; j < GB_K; ++j) {
+            const double v = (double)tile[threadIdx.y + i][(px + j) * 3 + c];
+#pragma unroll
+            for (int a = 0; a < GB_ANGLES; ++a) acc[a] = fma(c_gabor_taps[(a * GB_K + i) * GB_K + j], v, acc[a]);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int a = 0; a < GB_ANGLES; ++a) {
+        float p = (float)acc[a];                 // crossCorr converts its double result to the float plane
+        p = p > 1.f ? 1.f : p;                   // plane.setTo(1, plane > 1); plane.setTo(0, plane < 0)
+        p = p < 0.f ? 0.f : p;
+        sum = __fadd_rn(sum, p);                 // dst += plane
+    }
+    dst[(size_t)gy * dpitch + (size_t)gx * 3 + c] = __fmul_rn(sum, 1.f / GB_ANGLES);      // dst /= 16
+}
+
+// cv::getGaborKernel(Size(13, 13), sigma, theta, lambda, gamma, psi, CV_32F) (OCV imgproc/src/gabor.cpp:51-95)
+void gabor_kernel(double sigma, double theta, double lambd, double gamma, double psi, float* k) {
+    const double sigma_x = sigma, sigma_y = sigma / gamma, c = std::cos(theta), s = std::sin(theta);
+    const double ex = -0.5 / (sigma_x * sigma_x), ey = -0.5 / (sigma_y * sigma_y), cscale = 3.1415926535897932384626433832795 * 2 / lambd;
+    for (int y = -GB_R; y <= GB_R; ++y)
+        for (int x = -GB_R; x <= GB_R; ++x) {
+            const double xr = x * c + y * s, yr = -x * s + y * c;
+            const double v = 1.0 * std::exp(ex * xr * xr + ey * yr * yr) * std::cos(cscale * xr + psi);
+            k[(GB_R - y) * GB_K + (GB_R - x)] = (float)v;
+        }
+}
+
 thread_local std::string g_margin_error;
 int margin_fail(int code, const std::string& msg) {
     g_margin_error = msg;
@@ -162,6 +221,45 @@ int poppy_cuda_blur_margin(int device, const uint8_t* src, size_t src_step, int 
     MG_TRY(cudaMemcpy2D(dst, dst_step, d_out, pitch, pitch, union_h, cudaMemcpyDeviceToHost));
 #undef MG_TRY
     cudaFree(d_canvas); cudaFree(d_out); cudaFree(d_tmp);
+    return 0;
+}
+
+int poppy_cuda_gabor_filter(int device, const float* src, size_t src_step, int cols, int rows, float* dst, size_t dst_step) {
+    using namespace poppy;
+    if (!src || !dst || cols < 1 || rows < 1 || src_step < (size_t)cols * 12 || dst_step < (size_t)cols * 12 || src_step % 4 || dst_step % 4)
+        return margin_fail(POPPY_CUDA_ERR_INVALID, "gabor_filter: bad argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1 || device < 0 || device >= n_dev)
+        return margin_fail(POPPY_CUDA_ERR_NO_DEVICE, "gabor_filter: no such CUDA device (there is no CPU fallback)");
+    float *d_src = nullptr, *d_dst = nullptr;
+#define GB_TRY(expr)                                                                                                  \
+    do {                                                                                                              \
+        cudaError_t e_ = (expr);                                                                                      \
+        if (e_ != cudaSuccess) {                                                                                      \
+            cudaFree(d_src); cudaFree(d_dst);                                                                         \
+            return margin_fail(POPPY_CUDA_ERR_CUDA, std::string("gabor_filter: ") + cudaGetErrorString(e_));          \
+        }                                                                                                             \
+    } while (0)
+    GB_TRY(cudaSetDevice(device));
+    // the 16 kernels: theta_i = i * float(180 / 16) - an integer division, and degrees where radians are expected, as in the
+    // reference (src/util.cpp:43-46); sigma 5, lambda 10, gamma 0.04, psi pi/4 (src/util.hpp:95)
+    std::vector<double> taps((size_t)GB_ANGLES * GB_K * GB_K);
+    const float step = (float)(180 / GB_ANGLES);
+    for (int a = 0; a < GB_ANGLES; ++a) {
+        float k[GB_K * GB_K];
+        gabor_kernel(5.0, (double)(a * step), 10.0, 0.04, 3.1415926535897932384626433832795 / 4, k);
+        for (int i = 0; i < GB_K * GB_K; ++i) taps[(size_t)a * GB_K * GB_K + i] = (double)k[i];
+    }
+    GB_TRY(cudaMemcpyToSymbol(c_gabor_taps, taps.data(), taps.size() * sizeof(double)));
+    const size_t pitch = (size_t)cols * 3;
+    GB_TRY(cudaMalloc((void**)&d_src, pitch * rows * sizeof(float)));
+    GB_TRY(cudaMalloc((void**)&d_dst, pitch * rows * sizeof(float)));
+    GB_TRY(cudaMemcpy2D(d_src, pitch * 4, src, src_step, pitch * 4, rows, cudaMemcpyHostToDevice));
+    k_gabor<<<dim3(div_up(cols, GB_TW), div_up(rows, GB_TH)), dim3(3 * GB_TW, GB_TH)>>>(d_src, pitch, cols, rows, d_dst, pitch);
+    GB_TRY(cudaGetLastError());
+    GB_TRY(cudaMemcpy2D(dst, dst_step, d_dst, pitch * 4, pitch * 4, rows, cudaMemcpyDeviceToHost));
+#undef GB_TRY
+    cudaFree(d_src); cudaFree(d_dst);
     return 0;
 }
 
