@@ -1,12 +1,12 @@
 #!/usr/bin/env python
-"""Writes tests/golden/blur_margin.npz from the UNMODIFIED reference library (oracle/_ref/libpoppy_ref.so ->
+"""Writes tests/golden/conditioning/blur_margin.npz from the UNMODIFIED reference library (oracle/_ref/libpoppy_ref.so ->
 poppy::blur_margin, reference src/util.cpp:574-602). Run in the build container; the fixture travels, the reference does not."""
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
 from oracle import ref  # noqa: E402
 
 rng = np.random.default_rng(2024)

@@ -14,7 +14,7 @@ import pytest
 
 from oracle import margin, ref
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "blur_margin.npz")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "conditioning", "blur_margin.npz")
 # (rows, cols, union_h, union_w): both axes padded, one axis, none (1-pixel margins), tall/wide, margins wider than the padding
 CASES = [(100, 150, 120, 180), (100, 150, 100, 150), (200, 100, 200, 160), (90, 90, 150, 90), (333, 211, 400, 300),
          (64, 48, 70, 300), (500, 500, 512, 512)]
