@@ -66,7 +66,13 @@ REFOBJS=("$OBJ"/{util,draw,settings,face,extractor,matcher,transformer,procruste
 echo "built $OUT/poppy_ref_full"
 if [ -f "$ROOT/poppy_b200/libpoppy_cuda.so" ] && [ -f "$ROOT/integration/algo_b200.cpp" ]; then
   "${CXX[@]}" -DPOPPY_WITH_B200 -Dmorph_images=morph_images_b200 -c "$ROOT/integration/algo_b200.cpp" -o "$OBJ/algo_b200.o"
-  "${CXX[@]}" -DPOPPY_WITH_B200 "$HERE/ref_full_harness.cpp" "$OBJ/algo_b200.o" "${REFOBJS[@]}" "${LIBS[@]}" \
+  # the conditioning drop-in: src/util.cpp once more with its two functions renamed (the file is untouched), and the stub
+  if [ ! -f "$OBJ/util_ref.o" ]; then
+    "${CXX[@]}" -Dblur_margin=blur_margin_reference -Dgabor_filter=gabor_filter_reference -c "$REF/src/util.cpp" -o "$OBJ/util_ref.o"
+  fi
+  "${CXX[@]}" -Dblur_margin=blur_margin_b200 -Dgabor_filter=gabor_filter_b200 -c "$ROOT/integration/util_b200.cpp" -o "$OBJ/util_b200.o"
+  REFOBJS=("$OBJ"/{util_ref,draw,settings,face,extractor,matcher,transformer,procrustes,terminal,algo_ref}.o)
+  "${CXX[@]}" -DPOPPY_WITH_B200 "$HERE/ref_full_harness.cpp" "$OBJ/algo_b200.o" "$OBJ/util_b200.o" "${REFOBJS[@]}" "${LIBS[@]}" \
       -L"$ROOT/poppy_b200" -lpoppy_cuda -Wl,-rpath,'$ORIGIN/../../poppy_b200' -o "$OUT/poppy_dropin"
   echo "built $OUT/poppy_dropin"
 fi

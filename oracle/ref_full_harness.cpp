@@ -13,6 +13,10 @@
 //
 //   poppy_ref_full dump <config 1|2|3> <images dir> <out dir> [all|some]     (cwd = reference src/: face assets)
 //        runs the reference, writes the fixture files read by tests/golden/make_golden_full.py
+//   poppy_ref_full raw <config> <images dir> <dump dir>          adds the pre-canvas inputs to a dump (for `full`)
+//   poppy_dropin full <dump dir> [frames]
+//        the WHOLE pipeline from the raw inputs, all-reference and with blur_margin + gabor_filter + morph_images served by
+//        integration/{util,algo}_b200.cpp; compares the union canvases and every frame
 //   poppy_dropin replay <dump dir> <ref|b200|both> [frames]
 //        re-runs poppy::morph<Sink>() from the dumped union images (no /root/reference needed, configs without
 //        face detection) with the chosen morph_images body; `both` runs the chain twice and compares every frame
@@ -39,10 +43,19 @@ double morph_images_b200(const Mat& img1, const Mat& img2, const Mat& corrected1
                          Mat& goodFeatures1, Mat& goodFeatures2, Mat& dst, const Mat& last, vector<Point2f>& morphedPoints,
                          vector<Point2f> srcPoints1, vector<Point2f> srcPoints2, double shapeRatio, double maskRatio,
                          double linear);
+// poppy_dropin only: src/util.cpp is compiled with -Dblur_margin=blur_margin_reference -Dgabor_filter=gabor_filter_reference
+// and integration/util_b200.cpp with the _b200 renames; the interposers below route every call of the pipeline
+void blur_margin_reference(const Mat& src, const Size& szUnion, Mat& dst);
+void gabor_filter_reference(const Mat& src, Mat& dst, size_t numAngles, int kernel_size, double sig, double lm, double gm, double ps);
+void blur_margin_b200(const Mat& src, const Size& szUnion, Mat& dst);
+void gabor_filter_b200(const Mat& src, Mat& dst, size_t numAngles, int kernel_size, double sig, double lm, double gm, double ps);
 #endif
 }  // namespace poppy
 
 namespace {
+
+int g_cond = 0;                     // 0 reference blur_margin / gabor_filter, 1 integration/util_b200.cpp
+int g_cond_calls[2] = {0, 0};       // blur_margin / gabor_filter calls served by the B200 bodies
 
 struct Call {                       // one morph_images() call as seen at src/poppy.hpp:215
     double shape, mask, linear;
@@ -121,6 +134,21 @@ cv::Mat to_union(const cv::Mat& img, cv::Size sz) {
 }
 
 }  // namespace
+
+#ifdef POPPY_WITH_B200
+namespace poppy {
+void blur_margin(const Mat& src, const Size& szUnion, Mat& dst) {
+    if (g_cond) { ++g_cond_calls[0]; blur_margin_b200(src, szUnion, dst); }
+    else blur_margin_reference(src, szUnion, dst);
+}
+void gabor_filter(const Mat& src, Mat& dst, size_t numAngles, int kernel_size, double sig, double lm, double gm, double ps) {
+    // the morph path's call (src/poppy.hpp:122) uses the defaults; the extractor's 31 x 31 call is not on the path
+    const bool defaults = numAngles == 16 && kernel_size == 13 && sig == 5 && lm == 10 && gm == 0.04 && ps == CV_PI / 4;
+    if (g_cond && defaults) { ++g_cond_calls[1]; gabor_filter_b200(src, dst, numAngles, kernel_size, sig, lm, gm, ps); }
+    else gabor_filter_reference(src, dst, numAngles, kernel_size, sig, lm, gm, ps);
+}
+}  // namespace poppy
+#endif
 
 namespace poppy {
 // the interposer: src/poppy.hpp:215 calls this
@@ -294,11 +322,98 @@ int cmd_replay(int argc, char** argv) {
     return differing == 0 ? 0 : 1;
 }
 
+// the inputs of a config before the union canvas (what run() reads from disk, resized for config 3)
+bool load_raw(int cfg, const std::string& img_dir, cv::Mat& a, cv::Mat& b, cv::Size& sz) {
+    const Config& C = kConfigs[cfg];
+    a = cv::imread(img_dir + "/" + C.a, cv::IMREAD_COLOR);
+    b = cv::imread(img_dir + "/" + C.b, cv::IMREAD_COLOR);
+    if (a.empty() || b.empty()) return false;
+    if (C.scale_to) {
+        cv::Mat t;
+        cv::resize(a, t, cv::Size(C.scale_to, C.scale_to * a.rows / a.cols), 0, 0, cv::INTER_LINEAR); a = t.clone();
+        cv::resize(b, t, cv::Size(C.scale_to, C.scale_to * b.rows / b.cols), 0, 0, cv::INTER_LINEAR); b = t.clone();
+    }
+    sz = cv::Size(std::max(a.cols, b.cols), std::max(a.rows, b.rows));
+    if (C.canvas_w) sz = cv::Size(C.canvas_w, C.canvas_h);
+    return true;
+}
+
+// adds the pre-canvas inputs to an existing dump (raw1.u8, raw2.u8, raw.txt), for `full`
+int cmd_raw(int argc, char** argv) {
+    if (argc < 5) { fprintf(stderr, "usage: raw <config> <images dir> <dump dir>\n"); return 2; }
+    const int cfg = atoi(argv[2]);
+    if (cfg < 1 || cfg > 3) return 2;
+    cv::Mat a, b;
+    cv::Size sz;
+    if (!load_raw(cfg, argv[3], a, b, sz)) { fprintf(stderr, "cannot read the input images\n"); return 3; }
+    const std::string out = argv[4];
+    write_mat(out + "/raw1.u8", a); write_mat(out + "/raw2.u8", b);
+    std::ofstream f(out + "/raw.txt");
+    f << a.cols << " " << a.rows << " " << b.cols << " " << b.rows << " " << sz.width << " " << sz.height << "\n";
+    return 0;
+}
+
+// The reference's WHOLE pipeline from the raw inputs - blur_margin, extractor, matcher, gabor_filter, frame loop - run twice:
+// all-reference, and with blur_margin + gabor_filter (default-parameter call) + morph_images served by the B200 library.
+int cmd_full(int argc, char** argv) {
+    if (argc < 3) { fprintf(stderr, "usage: full <dump dir> [frames]\n"); return 2; }
+#ifndef POPPY_WITH_B200
+    fprintf(stderr, "this binary has no B200 bodies (build poppy_dropin)\n");
+    return 3;
+#else
+    const std::string dir = argv[2];
+    const Meta M = read_meta(dir);
+    int aw = 0, ah = 0, bw = 0, bh = 0, uw = 0, uh = 0;
+    { std::ifstream f(dir + "/raw.txt"); f >> aw >> ah >> bw >> bh >> uw >> uh; }
+    if (M.w <= 0 || M.face || aw <= 0) { fprintf(stderr, "bad dump (run `raw` first; face configs need the reference tree)\n"); return 3; }
+    const int frames = argc > 3 ? atoi(argv[3]) : M.frames;
+    cv::Mat a = read_mat(dir + "/raw1.u8", ah, aw, CV_8UC3), b = read_mat(dir + "/raw2.u8", bh, bw, CV_8UC3);
+    Sink sinks[2];
+    double secs[2] = {0, 0}, in_morph[2] = {0, 0};
+    long long canvas_diff = 0;
+    cv::Mat canvases[2][2];
+    for (int impl = 0; impl < 2; ++impl) {
+        g_cond = impl;
+        const auto t0 = std::chrono::steady_clock::now();
+        cv::Mat u1 = to_union(a, cv::Size(uw, uh)), u2 = to_union(b, cv::Size(uw, uh));
+        canvases[impl][0] = u1; canvases[impl][1] = u2;
+        secs[impl] = run_chain(u1, u2, M, frames, impl, sinks[impl], &in_morph[impl]);
+        secs[impl] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    g_cond = 0;
+    for (int k = 0; k < 2; ++k) canvas_diff += cv::norm(canvases[0][k], canvases[1][k], cv::NORM_L1) != 0;
+    long long differing = 0, total = 0;
+    int max_abs = 0, first_bad = -1;
+    if (sinks[0].frames.size() != sinks[1].frames.size()) { printf("{\"error\": \"frame counts differ\"}\n"); return 1; }
+    for (size_t j = 0; j < sinks[0].frames.size(); ++j) {
+        const cv::Mat &x = sinks[0].frames[j], &y = sinks[1].frames[j];
+        long long bad = 0;
+        for (int r = 0; r < x.rows; ++r) {
+            const uint8_t *px = x.ptr<uint8_t>(r), *py = y.ptr<uint8_t>(r);
+            for (int i = 0; i < x.cols * 3; ++i) {
+                const int d = abs((int)px[i] - (int)py[i]);
+                bad += d != 0;
+                max_abs = std::max(max_abs, d);
+            }
+        }
+        differing += bad; total += (long long)x.rows * x.cols * 3;
+        if (bad && first_bad < 0) first_bad = (int)j;
+    }
+    printf("{\"frames\": %zu, \"width\": %d, \"height\": %d, \"mode\": \"full pipeline: reference vs blur_margin + gabor_filter + morph_images on B200\", "
+           "\"differing_bytes\": %lld, \"bytes\": %lld, \"max_abs\": %d, \"first_differing_frame\": %d, \"canvases_differing\": %lld, "
+           "\"b200_blur_margin_calls\": %d, \"b200_gabor_filter_calls\": %d, \"reference_s\": %.3f, \"b200_s\": %.3f}\n",
+           sinks[0].frames.size(), uw, uh, differing, total, max_abs, first_bad, canvas_diff, g_cond_calls[0], g_cond_calls[1], secs[0], secs[1]);
+    return differing == 0 && canvas_diff == 0 ? 0 : 1;
+#endif
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
+    if (argc >= 2 && std::string(argv[1]) == "raw") return cmd_raw(argc, argv);
+    if (argc >= 2 && std::string(argv[1]) == "full") return cmd_full(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "dump") return cmd_dump(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "replay") return cmd_replay(argc, argv);
-    fprintf(stderr, "usage: %s dump|replay ...\n", argv[0]);
+    fprintf(stderr, "usage: %s dump|raw|replay|full ...\n", argv[0]);
     return 2;
 }

@@ -2,7 +2,8 @@
 
     bash oracle/build_ref_full.sh                                   # builds oracle/_ref/poppy_ref_full (reference TUs + vendored OpenCV)
     cd /root/reference/src && for c in 1 2 3; do \
-        /root/repo/oracle/_ref/poppy_ref_full dump $c /root/reference/images /root/repo/oracle/_ref/full/c$c $([ $c = 3 ] && echo some || echo all); done
+        /root/repo/oracle/_ref/poppy_ref_full dump $c /root/reference/images /root/repo/oracle/_ref/full/c$c $([ $c = 3 ] && echo some || echo all);
+        /root/repo/oracle/_ref/poppy_ref_full raw $c /root/reference/images /root/repo/oracle/_ref/full/c$c; done
     python tests/golden/make_golden_full.py                         # -> tests/golden/full/c{1,2,3}.npz
 
 The dumps under oracle/_ref/full/ (git-ignored, shipped to the GPU box) hold what poppy::morph<Sink>() handed to

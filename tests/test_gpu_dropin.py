@@ -47,3 +47,29 @@ def test_dropin_under_the_reference_frame_loop_config3_prefix(native_lib):
     needs ~0.5 s per 1080p frame; the whole 120-frame chain is covered by tests/test_gpu_configs.py)."""
     out, rc = _replay(3, 24)
     assert out["frames"] == 24 and out["differing_bytes"] == 0 and rc == 0, out
+
+
+def _full(config, frames):
+    d = os.path.join(DUMPS, f"c{config}")
+    if not os.path.exists(BIN) or not os.path.exists(os.path.join(d, "raw.txt")):
+        pytest.skip("oracle/_ref/poppy_dropin or the raw inputs of the dump are not shipped (oracle/build_ref_full.sh, `raw`)")
+    r = subprocess.run([BIN, "full", d, str(frames)], env=_env(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=1200)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines, (r.returncode, r.stdout[-500:], r.stderr[-1500:])
+    return json.loads(lines[-1]), r.returncode
+
+
+def test_whole_pipeline_with_all_three_gpu_entry_points_config1(native_lib):
+    """The reference's whole pipeline from the raw images (blur_margin, extractor, matcher, gabor_filter, frame loop) with
+    blur_margin + gabor_filter (integration/util_b200.cpp) + morph_images (integration/algo_b200.cpp) served by the library:
+    the union canvases and all 60 frames equal the all-reference run."""
+    out, rc = _full(1, 60)
+    assert out["frames"] == 60 and out["differing_bytes"] == 0 and out["canvases_differing"] == 0 and rc == 0, out
+    assert out["b200_blur_margin_calls"] == 2 and out["b200_gabor_filter_calls"] == 1, out
+
+
+def test_whole_pipeline_with_all_three_gpu_entry_points_config3_prefix(native_lib):
+    """cat -> dog at 1920x1080 with real margins (1080-wide inputs on a 1920-wide canvas), 16 frames."""
+    out, rc = _full(3, 16)
+    assert out["frames"] == 16 and out["differing_bytes"] == 0 and out["canvases_differing"] == 0 and rc == 0, out
