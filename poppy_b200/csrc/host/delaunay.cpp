@@ -9,7 +9,52 @@
 #include <thread>
 #include <unordered_map>
 
+#include <sys/mman.h>
+
+#include <cstdlib>
+
 namespace poppy {
+
+namespace {
+constexpr size_t kHugePage = 2u << 20, kHugeMin = 256u << 10;
+struct HugeCache {          // the blocks a thread freed last (one per size class seen), reused by its next mesh
+    static constexpr int kSlots = 4;
+    void* ptr[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    size_t size[kSlots] = {0, 0, 0, 0};
+    ~HugeCache() { for (void* p : ptr) std::free(p); }
+};
+thread_local HugeCache g_huge_cache;
+size_t huge_round(size_t bytes) { return (bytes + kHugePage - 1) / kHugePage * kHugePage; }
+}  // namespace
+
+void* huge_alloc(size_t bytes) {
+    if (bytes < kHugeMin) {
+        void* p = std::malloc(bytes ? bytes : 1);
+        if (!p) throw std::bad_alloc();
+        return p;
+    }
+    const size_t size = huge_round(bytes);
+    HugeCache& c = g_huge_cache;
+    for (int i = 0; i < HugeCache::kSlots; ++i)
+        if (c.ptr[i] && c.size[i] == size) { void* p = c.ptr[i]; c.ptr[i] = nullptr; return p; }
+    void* p = std::aligned_alloc(kHugePage, size);
+    if (!p) throw std::bad_alloc();
+    static const bool advise = [] { const char* e = std::getenv("POPPY_PLAN_HUGEPAGES"); return !(e && e[0] == '0'); }();   // A/B switch
+    if (advise) madvise(p, size, MADV_HUGEPAGE);          // advisory: ordinary pages serve equally well, only slower
+    return p;
+}
+
+void huge_free(void* p, size_t bytes) {
+    if (!p) return;
+    if (bytes < kHugeMin) { std::free(p); return; }
+    HugeCache& c = g_huge_cache;
+    const size_t size = huge_round(bytes);
+    for (int i = 0; i < HugeCache::kSlots; ++i)
+        if (!c.ptr[i]) { c.ptr[i] = p; c.size[i] = size; return; }
+    std::free(c.ptr[0]);                      // cache full: drop the oldest entry
+    for (int i = 0; i + 1 < HugeCache::kSlots; ++i) { c.ptr[i] = c.ptr[i + 1]; c.size[i] = c.size[i + 1]; }
+    c.ptr[HugeCache::kSlots - 1] = p; c.size[HugeCache::kSlots - 1] = size;
+}
 
 void clip_points(std::vector<Point2f>& pts, int cols, int rows) {
     for (Point2f& p : pts) {

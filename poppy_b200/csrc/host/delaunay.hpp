@@ -11,6 +11,7 @@
 
 #include <atomic>
 #include <climits>
+#include <cstddef>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -58,6 +59,23 @@ struct WalkTrace {
 struct WalkPace {
     const std::atomic<int>* follow = nullptr;
     std::atomic<int>* publish = nullptr;
+};
+
+// Allocator of the mesh tables: blocks of 256 KB and more are 2 MB-aligned and advised as transparent huge pages, so that the
+// point-location walk - one dependent load into the 1.9 MB quad table per step - stops missing the first-level TLB (4 KB
+// pages cover 384 KB of it); the last block a thread freed is kept for its next mesh (a fresh block is zero-filled by the
+// kernel on first touch). Falls back to ordinary pages wherever the kernel does not grant huge ones.
+void* huge_alloc(size_t bytes);
+void huge_free(void* p, size_t bytes);
+template <class T>
+struct HugeAlloc {
+    using value_type = T;
+    HugeAlloc() = default;
+    template <class U> HugeAlloc(const HugeAlloc<U>&) {}
+    T* allocate(size_t n) { return static_cast<T*>(huge_alloc(n * sizeof(T))); }
+    void deallocate(T* p, size_t n) { huge_free(p, n * sizeof(T)); }
+    template <class U> bool operator==(const HugeAlloc<U>&) const { return true; }
+    template <class U> bool operator!=(const HugeAlloc<U>&) const { return false; }
 };
 
 class DelaunayMesh {
@@ -155,9 +173,9 @@ private:
     int side_of(Point2f p, int e) const;      // sign of "p is right of e" (primal edges only)
     Where classify(const Walk& w, int& edge, int& vertex);
 
-    std::vector<Quad> q_;
-    std::vector<int> org_;      // 2 per quad: origin vertex of edges 4q and 4q + 2
-    std::vector<Point2f> pt_;
+    std::vector<Quad, HugeAlloc<Quad>> q_;
+    std::vector<int, HugeAlloc<int>> org_;      // 2 per quad: origin vertex of edges 4q and 4q + 2
+    std::vector<Point2f, HugeAlloc<Point2f>> pt_;
     int free_quad_ = 0;
     int recent_ = 0;
     Point2f top_left_{0, 0}, bottom_right_{0, 0};
