@@ -633,6 +633,26 @@ def main():
                                                  "unmodified reference morph_images() on all host threads"}
                 out["parity_vs_reference"] = {"frames": len(idx), "differing_bytes": diff_bytes, "max_abs": worst,
                                               "min_fraction_within_1": within1}
+                # how much of the frame takes the median / sharpen branch of the dense unsharp kernel (its speed is data
+                # dependent): from the reference's own lapBlend of one sampled frame, x - GaussianBlur(x, sigma 1) against the
+                # kernel's group test (a 4-pixel group is flagged when any |diff| >= 0.17; a group runs the exact median when a
+                # flagged group touches its 3x3 windows)
+                try:
+                    st = ref.stages(job.bgr1, job.bgr2, job.gabor2, job.pts1, job.pts2, float(phases[idx[0]]), float(phases[idx[0]]), L)
+                    dmag = np.abs(st.lap_blend - ref.gaussian_blur(st.lap_blend, 1.0)).max(axis=2)
+                    wg = (W // 4) * 4
+                    grp = (dmag[:, :wg].reshape(H, wg // 4, 4) >= 0.17).any(axis=2)
+                    near = grp.copy()
+                    near[:, 1:] |= grp[:, :-1]; near[:, :-1] |= grp[:, 1:]
+                    med = near.copy()
+                    med[1:] |= near[:-1]; med[:-1] |= near[1:]
+                    out["unsharp"]["dense_kernel_branching"] = {
+                        "frame_phase": round(float(phases[idx[0]]), 3),
+                        "pixels_over_0.17": float((dmag >= 0.17).mean()), "groups_flagged": float(grp.mean()),
+                        "groups_running_the_median": float(med.mean()),
+                        "pixels_sharpened": float((st.dst != np.clip(np.rint(st.lap_blend * 255.0), 0, 255).astype(np.uint8)).any(axis=2).mean())}
+                except Exception as e:      # diagnostics only
+                    out["unsharp"]["dense_kernel_branching"] = {"error": str(e)[:200]}
                 if args.kprocs:
                     r.close()               # give the host memory back before K processes load the pair
                     out["cpu_baseline"]["k_process"] = kprocess_baseline(job, args.kprocs)

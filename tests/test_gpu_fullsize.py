@@ -99,3 +99,30 @@ def test_4k_overlapping_lanes_are_deterministic(workload):
             if ref_sums is None:
                 ref_sums = sums
             assert sums == ref_sums, f"run {run}: frames {[k for k in range(64) if sums[k] != ref_sums[k]]} changed"
+
+
+def test_8k_frame_matches_reference(native_lib):
+    """BASELINE.json configs[4] shape: 7680x4320, 50,004 points, 6 levels - one frame against the reference library (which
+    needs ~10 s for it) and the chunk-size independence of a 3-frame render through the device checksum."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("reference library not shipped")
+    from poppy_b200.renderer import MorphRenderer
+    c = synth.WORKLOADS["8k"]
+    inp = synth.make_inputs(c["w"], c["h"], c["n_points"], c["jitter"], c["seed"])
+    w, h, L = c["w"], c["h"], c["levels"]
+    phases = np.array([0.37, 0.5, 0.93], np.float32)
+    plan = host.SequencePlan(inp.pts1, inp.pts2, w, h, phases)
+    sums = []
+    for chunk in (3, 1):
+        with MorphRenderer(w, h, L, len(inp.pts1), plan.max_triangles, 3, chunk_frames=chunk) as r:
+            r.set_pair(inp.bgr1, inp.bgr2, inp.gabor2)
+            r.set_points(inp.pts1, inp.pts2)
+            r.render(phases, phases.astype(np.float64), plan.tri_idx, plan.tri_offsets)
+            sums.append(r.checksum(0, 3))
+            if chunk == 3:
+                frame = r.download(0, 1)[0]
+    assert sums[0] == sums[1], "8K frames depend on the chunk size"
+    want, _ = ref.morph_images(inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, float(phases[0]), float(phases[0]), L)
+    rep = assert_frame_parity(frame, want, "8K phase 0.37")
+    assert rep["differing_bytes"] == 0, rep
