@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import threading
+
 import numpy as np
 
 from . import host
@@ -94,10 +96,24 @@ def morph_images(img1, img2, corrected1, corrected2, gabor2, src_points1, src_po
     if p1.shape != p2.shape:
         raise ValueError("point sets differ in size")          # assert at src/algo.cpp:51
     morphed = host.morph_points(p1, p2, shape_ratio, w, h)     # host copy, needed for the topology
-    tri = host.triangulate(morphed, w, h, sequential=True)
-    r = _renderer(w, h, len(p1), len(tri), 1)
-    r.set_pair(np.ascontiguousarray(corrected1), np.ascontiguousarray(corrected2), np.ascontiguousarray(gabor2))
-    r.set_points(p1, p2)
+    r = _renderer(w, h, len(p1), 2 * len(p1) + 16, 1)          # sized for the most triangles these points can give
+    # the pair travels to the device (150 MB at 4K) while this thread triangulates; both are C calls that release the GIL
+    failure = []
+
+    def upload():
+        try:
+            r.set_pair(np.ascontiguousarray(corrected1), np.ascontiguousarray(corrected2), np.ascontiguousarray(gabor2))
+            r.set_points(p1, p2)
+        except Exception as e:      # re-raised on the calling thread
+            failure.append(e)
+    t = threading.Thread(target=upload)
+    t.start()
+    try:
+        tri = host.triangulate(morphed, w, h, sequential=True)
+    finally:
+        t.join()
+    if failure:
+        raise failure[0]
     r.render([shape_ratio], [mask_ratio], tri, [0, len(tri)])
     dst = r.download(0, 1)[0]
     return dst, r.morphed_points(0)

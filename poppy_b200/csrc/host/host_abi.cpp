@@ -268,16 +268,23 @@ int poppy_morph_images(poppy_cuda_ctx* ctx, const uint8_t* c1, size_t step1, con
     poppy::clip_points(b, w, h);
     const float s = (float)shape_ratio;
     lerp_points(a, b, s, w, h, m);
+    // the pair travels to the device (pageable host memory: ~150 MB at 4K) while this thread triangulates
+    int rc_up = 0;
+    std::thread upload([&] {
+        rc_up = poppy_cuda_set_pair(ctx, c1, step1, c2, step2, gabor2, gstep);
+        if (rc_up == 0) rc_up = poppy_cuda_set_points(ctx, sp1, sp2, n);
+    });
     std::vector<int32_t> tri;
     std::string err;
     // the reference calls morph_images() once per frame of a sequence: the previous call's point-location walks predict this
     // call's (poppy::WalkTrace; any guide gives the same triangulation)
-    if (!poppy::triangulate_points_next(m, w, h, tri, &err)) return host_fail(POPPY_CUDA_ERR_INVALID, err);
+    const bool tri_ok = poppy::triangulate_points_next(m, w, h, tri, &err);
+    upload.join();
+    if (!tri_ok) return host_fail(POPPY_CUDA_ERR_INVALID, err);
+    if (rc_up != 0) return host_fail(rc_up, poppy_cuda_last_error(ctx));
     const int32_t offs[2] = {0, (int32_t)(tri.size() / 3)};
     int rc;
-    if ((rc = poppy_cuda_set_pair(ctx, c1, step1, c2, step2, gabor2, gstep)) != 0 ||
-        (rc = poppy_cuda_set_points(ctx, sp1, sp2, n)) != 0 ||
-        (rc = poppy_cuda_render(ctx, 1, &s, &mask_ratio, tri.data(), offs, 0)) != 0 ||
+    if ((rc = poppy_cuda_render(ctx, 1, &s, &mask_ratio, tri.data(), offs, 0)) != 0 ||
         (rc = poppy_cuda_download(ctx, 0, 1, dst, dst_step, dst_step * (size_t)h)) != 0 ||
         (morphed_xy && (rc = poppy_cuda_get_morphed_points(ctx, 0, morphed_xy)) != 0) ||
         (rc = poppy_cuda_sync(ctx)) != 0)

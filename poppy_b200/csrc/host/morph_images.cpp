@@ -4,6 +4,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <thread>
 
 #include "../../../include/poppy_host.h"
 
@@ -77,15 +78,21 @@ double morph_images(const Image8& img1, const Image8& /*img2*/, const Image8& co
     const float* p2 = n ? &srcPoints2.data()->x : none;
     float* mp = n ? &morphedPoints.data()->x : nullptr;
     if (n) poppy_host_morph_points(p1, p2, n, shapeRatio, w, h, mp);
+    std::lock_guard<std::mutex> lock(g_mu);
+    // sized for the most triangles n points can give, so that the pair can travel to the device while this thread triangulates
+    poppy_cuda_ctx* c = context_for(w, h, (int)Settings::instance().pyramid_levels, n, 2 * n + 16, 1);
+    int rc_up = 0;
+    std::thread upload([&] {
+        rc_up = poppy_cuda_set_pair(c, corrected1.data, corrected1.step, corrected2.data, corrected2.step, gabor2.data, gabor2.step);
+        if (rc_up == 0) rc_up = poppy_cuda_set_points(c, p1, p2, n);
+    });
     std::vector<int32_t> tri;
     std::string err;
-    if (!triangulate_points_next(morphedPoints, w, h, tri, &err)) throw MorphError("morph_images: " + err);
+    const bool tri_ok = triangulate_points_next(morphedPoints, w, h, tri, &err);
+    upload.join();
+    if (!tri_ok) throw MorphError("morph_images: " + err);
+    cu(c, rc_up);
     const int n_tri = (int)tri.size() / 3;
-
-    std::lock_guard<std::mutex> lock(g_mu);
-    poppy_cuda_ctx* c = context_for(w, h, (int)Settings::instance().pyramid_levels, n, n_tri, 1);
-    cu(c, poppy_cuda_set_pair(c, corrected1.data, corrected1.step, corrected2.data, corrected2.step, gabor2.data, gabor2.step));
-    cu(c, poppy_cuda_set_points(c, p1, p2, n));
     const float s = (float)shapeRatio;
     const int32_t offs[2] = {0, n_tri};
     cu(c, poppy_cuda_render(c, 1, &s, &maskRatio, tri.data(), offs, 0));

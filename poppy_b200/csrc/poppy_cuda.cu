@@ -126,6 +126,7 @@ struct poppy_cuda_ctx {
     int l0_chunk_rows = 0;                   // POPPY_CUDA_US_ROWS: rows per CTA of the dense unsharp pass (0: 216)
     double calm_share = 1.0;                 // running share of flagged strip chunks (starts pessimistic: dense until a scan says otherwise)
     unsigned route_tick = kCalmProbeEvery - 1;   // the first dense chunk carries a scan
+    unsigned probe_every = kCalmProbeEvery;      // backs off (x2, up to 64) while the scans keep reporting busy content
     int mm_pitch = 0;                        // blocks per row of the clamp-excess table, padded
     size_t mm_stride = 0;
     unsigned long long* d_calm_total = nullptr;      // flagged strip chunks since the last stats read
@@ -348,6 +349,8 @@ void harvest_calm_stats(poppy_cuda_ctx* c, bool wait) {
         for (int i = 0; i < l.calm_pending; ++i) flagged += l.h_calm_counts[i];
         const double share = (double)flagged / ((double)l.calm_pending * chunks_per_frame);
         c->calm_share = 0.5 * c->calm_share + 0.5 * share;
+        // content that keeps flagging most chunks is probed less and less often; anything calmer resets the interval
+        c->probe_every = share > 0.5 ? std::min(c->probe_every * 2, 64u) : kCalmProbeEvery;
         l.calm_pending = 0;
     }
 }
@@ -479,7 +482,7 @@ int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* s
             }
         }
         c->dense_chunks_total += (uint64_t)nb * chunks_per_frame;
-        if (c->unsharp_mode == 0 && !c->keep_stages && (++c->route_tick % kCalmProbeEvery) == 0 && !ln.calm_pending) {
+        if (c->unsharp_mode == 0 && !c->keep_stages && (++c->route_tick % c->probe_every) == 0 && !ln.calm_pending) {
             // statistic only: the byte scan of the finished frames (no clamp-excess information on this route)
             Scope s(c, KC_CALM, st);
             c->launches += 2;
