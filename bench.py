@@ -638,7 +638,8 @@ def main():
                 # kernel's group test (a 4-pixel group is flagged when any |diff| >= 0.17; a group runs the exact median when a
                 # flagged group touches its 3x3 windows)
                 try:
-                    st = ref.stages(job.bgr1, job.bgr2, job.gabor2, job.pts1, job.pts2, float(phases[idx[0]]), float(phases[idx[0]]), L)
+                    kmid = min(idx, key=lambda k: abs(float(phases[k]) - 0.5))        # the sampled frame nearest mid-morph
+                    st = ref.stages(job.bgr1, job.bgr2, job.gabor2, job.pts1, job.pts2, float(phases[kmid]), float(phases[kmid]), L)
                     dmag = np.abs(st.lap_blend - ref.gaussian_blur(st.lap_blend, 1.0)).max(axis=2)
                     wg = (W // 4) * 4
                     grp = (dmag[:, :wg].reshape(H, wg // 4, 4) >= 0.17).any(axis=2)
@@ -647,7 +648,7 @@ def main():
                     med = near.copy()
                     med[1:] |= near[:-1]; med[:-1] |= near[1:]
                     out["unsharp"]["dense_kernel_branching"] = {
-                        "frame_phase": round(float(phases[idx[0]]), 3),
+                        "frame_phase": round(float(phases[kmid]), 3),
                         "pixels_over_0.17": float((dmag >= 0.17).mean()), "groups_flagged": float(grp.mean()),
                         "groups_running_the_median": float(med.mean()),
                         "pixels_sharpened": float((st.dst != np.clip(np.rint(st.lap_blend * 255.0), 0, 255).astype(np.uint8)).any(axis=2).mean())}
