@@ -110,8 +110,8 @@ struct poppy_cuda_ctx {
         std::vector<CollapseMaps> maps;      // tensor maps of level k's collapse (index k); empty = no TMA path
         FrameParams* h_fp = nullptr;         // pinned staging
         int32_t* h_tri = nullptr;
-    } lane[4];
-    int want_lanes = 3;                      // POPPY_CUDA_LANES (1..4)
+    } lane[8];
+    int want_lanes = 4;                      // POPPY_CUDA_LANES (1..8); measured at 4K: 1 lane 2,694, 2: 2,952, 3: 3,150, 4: 3,219-3,259, 8: 3,263 frames/s
     int n_lanes = 0;                         // lanes allocated (0 = none yet)
     int n_tiles = 0, list_cap = 0;
     // levels tail_k0 .. L run in one launch (k_pyramid_tail); 0 = none (no level is small enough, or POPPY_CUDA_TAIL=0)
@@ -535,7 +535,7 @@ int poppy_cuda_create(poppy_cuda_ctx** out, int device, int width, int height, i
     c->device = device; c->w = width; c->h = height; c->levels = pyramid_levels;
     c->max_points = max_points; c->max_tri = max_triangles; c->max_frames = max_batch_frames;
     if (const char* e = std::getenv("POPPY_CUDA_SINGLE_LANE")) c->single_lane = e[0] == '1';   // A/B switch for profiling
-    if (const char* e = std::getenv("POPPY_CUDA_LANES")) c->want_lanes = std::max(1, std::min(4, std::atoi(e)));
+    if (const char* e = std::getenv("POPPY_CUDA_LANES")) c->want_lanes = std::max(1, std::min(8, std::atoi(e)));
     if (const char* e = std::getenv("POPPY_CUDA_L0_GROUP")) c->l0_group = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("POPPY_CUDA_US_ROWS")) c->l0_chunk_rows = std::max(0, std::atoi(e)) / 8 * 8;
     auto bail = [&](int rc) { g_create_error = c->err; poppy_cuda_destroy(c); return rc; };
