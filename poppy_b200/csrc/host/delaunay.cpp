@@ -303,16 +303,21 @@ inline int64_t area_bits(const float* opt, __m128d P) {
 }  // namespace
 
 void DelaunayMesh::walk_guided(Walk& w, const uint64_t* bits, uint32_t first, int count, MoveLog* log) const {
-    if (w.r_cur == 0 || count <= 0) return;
+    if (w.r_cur == 0 || count <= 0 || w.budget <= 0) return;
     const Quad* __restrict__ q = q_.data();
     const __m128d P = _mm_set_pd((double)w.p.y, (double)w.p.x);
-    int e = w.e, budget = w.budget, wrong = 0;
-    bool moved = false;
-    MoveLog lg;
-    if (log) lg = *log;
-    for (int j = 0; j < count && budget > 0; ++j) {
-        const uint32_t b = first + (uint32_t)j;
-        const int bit = (int)((__atomic_load_n(&bits[b >> 6], __ATOMIC_RELAXED) >> (b & 63)) & 1);
+    const int steps = std::min(count, w.budget);
+    int e = w.e, j = 0;
+    // the guide's bits pass through one register; the moves taken are appended to the log in bulk afterwards (they are
+    // the guide's bits except at the - at most 9 - steps noted in wrong_at)
+    uint64_t word = __atomic_load_n(&bits[first >> 6], __ATOMIC_RELAXED) >> (first & 63);
+    int left = 64 - (int)(first & 63);
+    uint16_t wrong_at[kMaxWrong + 1];
+    int wrong = 0;
+    for (; j < steps; ++j) {
+        const int bit = (int)(word & 1);
+        word >>= 1;
+        if (--left == 0) { word = __atomic_load_n(&bits[(first + (uint32_t)j + 1) >> 6], __ATOMIC_RELAXED); left = 64; }
         const Quad& qe = q[e >> 2];
         const int on = qe.next[e & 3], dp = rot(qe.next[(e + 3) & 3], 3);
         int nxt = bit ? dp : on;                // the only value the next step's loads wait for
@@ -330,18 +335,33 @@ void DelaunayMesh::walk_guided(Walk& w, const uint64_t* bits, uint32_t first, in
             // rejoin a step or two later with the same number of moves, so the following bits still apply
             asm volatile("" ::: "memory");      // keeps this a branch: as a conditional move it would tie nxt to the predicates
             nxt = g_on ? dp : on;
-            ++wrong;
+            wrong_at[wrong++] = (uint16_t)j;
+            if (wrong > kMaxWrong) { e = nxt; ++j; break; }              // the guide no longer describes this walk
         }
-        --budget;
-        lg.push(g_on);
         e = nxt;
-        moved = true;
-        if (__builtin_expect(wrong > 8, 0)) break;                       // the guide no longer describes this walk
     }
+    if (j == 0) return;
     w.e = e;
-    w.budget = budget;
-    if (moved) w.r_cur = -1;
-    if (log) *log = lg;
+    w.budget -= j;
+    w.r_cur = -1;
+    if (log) log->append(bits, first, j, wrong_at, wrong);
+}
+
+// n moves = bits first .. first + n - 1 of src with the positions listed in flips inverted
+void DelaunayMesh::MoveLog::append(const uint64_t* src, uint32_t first, int n, const uint16_t* flips, int n_flips) {
+    if (!t) return;
+    int f = 0;
+    for (int done = 0; done < n && pos < limit;) {
+        const uint32_t sb = first + (uint32_t)done;
+        const int take = std::min({n - done, 64 - (int)(sb & 63), 64 - (int)(pos & 63), (int)(limit - pos)});
+        uint64_t chunk = __atomic_load_n(&src[sb >> 6], __ATOMIC_RELAXED) >> (sb & 63);
+        if (take < 64) chunk &= (1ull << take) - 1;
+        while (f < n_flips && (int)flips[f] < done + take) { chunk ^= 1ull << (flips[f] - done); ++f; }
+        acc |= chunk << (pos & 63);
+        pos += (uint32_t)take;
+        done += take;
+        if ((pos & 63) == 0) { __atomic_store_n(&t->bits[(pos >> 6) - 1], acc, __ATOMIC_RELAXED); acc = 0; }
+    }
 }
 
 bool DelaunayMesh::walk_run(Walk& w) const { return walk_run(w, nullptr); }

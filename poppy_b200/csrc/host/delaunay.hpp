@@ -127,10 +127,12 @@ public:
             acc |= (uint64_t)bit << (pos & 63);
             if ((++pos & 63) == 0) { __atomic_store_n(&t->bits[(pos >> 6) - 1], acc, __ATOMIC_RELAXED); acc = 0; }
         }
+        void append(const uint64_t* src, uint32_t first, int n, const uint16_t* flips, int n_flips);
         void stop() { limit = pos; }            // a degenerate step: what follows is not a prefix of general-position moves
         void close();
     };
     bool walk_run(Walk& w, MoveLog* log) const;
+    static constexpr int kMaxWrong = 8;         // wrong predictions after which a walk gives up on its guide
     // Follows up to `count` predicted moves (bits first .. first + count - 1 of `bits`), verifying each; stops in front of
     // the first step whose predicates disagree with the prediction (or end the walk, or are degenerate).
     void walk_guided(Walk& w, const uint64_t* bits, uint32_t first, int count, MoveLog* log) const;
