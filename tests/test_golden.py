@@ -46,3 +46,14 @@ def test_port_reproduces_golden_chain():
         assert bits_differ(st.morphed_points, g["points"][j]) == 0, j
         assert (st.dst == g["frames"][j]).all(), j
         cur_img, cur_pts = st.dst, st.morphed_points
+
+
+def test_fixtures_come_from_the_avx2_fma_dispatch_of_the_reference():
+    """Bit parity is defined against the reference's AVX2/FMA-dispatched OpenCV build: the whole-pipeline
+    fixtures record the CPU features the reference ran with when they were made."""
+    import os
+    import numpy as np
+    full = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full")
+    for c in (1, 2, 3):
+        feats = str(np.load(os.path.join(full, f"c{c}.npz"))["cpu_features"])
+        assert "AVX2" in feats and "FP16" in feats, feats

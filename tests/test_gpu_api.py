@@ -304,3 +304,29 @@ def test_sliced_chain_continues_across_render_calls(native_lib):
     plan.close()
     for j in range(N):
         assert bits_differ(frames[j], g["frames"][j]) == 0, f"chain frame {j}"
+
+
+def test_two_contexts_on_two_devices_in_one_process(native_lib):
+    """The > 48 KB dynamic shared memory opt-in is per device: a context on device 1 after one on device 0
+    must render the same frame. Skipped on a single-GPU box."""
+    import ctypes as C
+    n = C.c_int(0)
+    try:
+        C.CDLL("libcudart.so").cudaGetDeviceCount(C.byref(n))
+    except OSError:
+        import torch
+        n.value = torch.cuda.device_count()
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    from poppy_b200 import api, synth
+    inp = synth.block_inputs(320, 200, 60, seed=21)
+    frames = []
+    for dev in (0, 1, 0):
+        s = api.Settings.instance()
+        s.cuda_device, s.pyramid_levels = dev, 5
+        dst, _ = api.morph_images(inp.bgr1, inp.bgr2, inp.bgr1, inp.bgr2, inp.gabor2, inp.pts1, inp.pts2, 0.35, 0.6)
+        frames.append(dst)
+        api.release()
+        assert (api.blur_margin(inp.bgr1[:150, :300], (320, 200)) == api.blur_margin(inp.bgr1[:150, :300], (320, 200))).all()
+    api.Settings.instance().cuda_device = 0
+    assert (frames[0] == frames[1]).all() and (frames[0] == frames[2]).all()
