@@ -63,3 +63,19 @@ def test_kernels_are_compiled_for_sm_100a(native_lib):
         pytest.skip("cuobjdump not available")
     out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_conditioning_entry_points_fail_loudly_without_a_gpu(native_lib):
+    """poppy_cuda_blur_margin / poppy_cuda_gabor_filter have no CPU fallback either (only checked where no GPU is visible)."""
+    import numpy as np
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is visible")
+    except ImportError:
+        pass
+    from poppy_b200 import api
+    with pytest.raises(RuntimeError, match="no such CUDA device|CUDA"):
+        api.blur_margin(np.zeros((40, 50, 3), np.uint8), (60, 50))
+    with pytest.raises(RuntimeError, match="no such CUDA device|CUDA"):
+        api.gabor_filter(np.zeros((40, 50, 3), np.float32))
