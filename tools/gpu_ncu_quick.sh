@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 TAG=${1:-q}
 timeout 900 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread \
-  --clock-control none -s ${NCU_SKIP:-40} -c ${NCU_COUNT:-40} --csv --log-file gpurun_out/ncu_quick_${TAG}.csv \
+  --clock-control none ${NCU_KERNEL:+-k regex:$NCU_KERNEL} -s ${NCU_SKIP:-40} -c ${NCU_COUNT:-40} --csv --log-file gpurun_out/ncu_quick_${TAG}.csv \
   python bench.py --frames 32 --steps 1 --warmup 1 --cpu-frames 0 --e2e-steps 0 --no-stage-pass ${BENCH_ARGS:---unsharp-mode 1} > gpurun_out/ncu_quick_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_quick_${TAG}.log
 python - <<EOF
