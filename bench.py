@@ -540,7 +540,11 @@ def main():
 
     # ---- reduce over ranks ---------------------------------------------------------------------------------------
     frames_all = F
+    rank_ms = [dev_ms / args.steps]
     if world > 1:
+        per_rank = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(per_rank, torch.tensor([dev_ms / args.steps], dtype=torch.float64, device="cuda"))
+        rank_ms = [float(v[0]) for v in per_rank]
         t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s = float(t[0]), float(t[1])
@@ -571,7 +575,8 @@ def main():
                              "launches_per_step": v["launches"], "us_per_launch": round(1000 * v["ms"] / v["launches"], 2)})
         out = {
             "metric": "morphed frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": job.scaling,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "ms_per_step_by_rank": [round(v, 2) for v in rank_ms],
+            "higher_is_better": True, "scaling": job.scaling,
             "vs_baseline": None, "dtype": "u8/f32", "data": job.data,
             "config": job.config(),
             "e2e": {"value": frames_all / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_bytes),
