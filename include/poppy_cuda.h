@@ -121,6 +121,14 @@ int poppy_cuda_render(poppy_cuda_ctx* ctx, int n_frames, const float* shape_rati
 int poppy_cuda_render_range(poppy_cuda_ctx* ctx, int first_slot, int n_frames, const float* shape_ratio,
                             const double* mask_ratio, const int32_t* tri_idx, const int32_t* tri_offsets, int chain);
 
+/* Resident plan: the packed triangle lists of a whole sequence (the layout poppy_cuda_render takes) copied to HBM and
+ * validated once, after poppy_cuda_set_points. poppy_cuda_render_planned then renders plan frames
+ * [plan_first, plan_first + n_frames) into ring slots first_slot.. with shape_ratio / mask_ratio indexed from 0 for the call -
+ * no per-render staging of the lists (at 4K / 20k points they are 290 MB per 600 frames). A new point set invalidates the plan. */
+int poppy_cuda_set_plan(poppy_cuda_ctx* ctx, const int32_t* tri_idx, const int32_t* tri_offsets, int n_frames);
+int poppy_cuda_render_planned(poppy_cuda_ctx* ctx, int first_slot, int plan_first, int n_frames, const float* shape_ratio,
+                              const double* mask_ratio, int chain);
+
 /* Copy frames [first, first+count) (8UC3 BGR) to host memory: row stride `step` bytes, `frame_stride` bytes
  * between frames. Ordered after every render queued so far, on a separate copy stream (renders of other slots are not
  * held up; a render of slots with a download pending waits for it). Asynchronous if dst is pinned;

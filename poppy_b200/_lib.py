@@ -68,6 +68,8 @@ def load():
         "poppy_cuda_set_points": (i32, [vp, vp, vp, i32]),
         "poppy_cuda_render": (i32, [vp, i32, vp, vp, vp, vp, i32]),
         "poppy_cuda_render_range": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
+        "poppy_cuda_set_plan": (i32, [vp, vp, vp, i32]),
+        "poppy_cuda_render_planned": (i32, [vp, i32, i32, i32, vp, vp, i32]),
         "poppy_cuda_download": (i32, [vp, i32, i32, vp, C.c_size_t, C.c_size_t]),
         "poppy_cuda_download_async": (i32, [vp, i32, i32, vp, C.c_size_t, C.c_size_t, u64p]),
         "poppy_cuda_download_wait": (i32, [vp, C.c_uint64]),
@@ -100,7 +102,7 @@ def load():
 CUDA_ABI_SYMBOLS = [
     "poppy_cuda_device_count", "poppy_cuda_create", "poppy_cuda_destroy", "poppy_cuda_set_keep_stages",
     "poppy_cuda_set_chunk_frames", "poppy_cuda_set_stage_timing", "poppy_cuda_set_pair", "poppy_cuda_set_points",
-    "poppy_cuda_render", "poppy_cuda_render_range", "poppy_cuda_download", "poppy_cuda_get_morphed_points",
+    "poppy_cuda_render", "poppy_cuda_render_range", "poppy_cuda_set_plan", "poppy_cuda_render_planned", "poppy_cuda_download", "poppy_cuda_get_morphed_points",
     "poppy_cuda_frame_device_ptr",
     "poppy_cuda_checksum", "poppy_cuda_sync", "poppy_cuda_get_stream", "poppy_cuda_last_render_ms",
     "poppy_cuda_launch_count", "poppy_cuda_stage_times", "poppy_cuda_debug_read", "poppy_cuda_last_error",

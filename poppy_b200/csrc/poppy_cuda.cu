@@ -126,7 +126,12 @@ struct poppy_cuda_ctx {
     int l0_chunk_rows = 0;                   // POPPY_CUDA_US_ROWS: rows per CTA of the dense unsharp pass (0: 216)
     double calm_share = 1.0;                 // running share of flagged strip chunks (starts pessimistic: dense until a scan says otherwise)
     unsigned route_tick = kCalmProbeEvery - 1;   // the first dense chunk carries a scan
-    unsigned probe_every = kCalmProbeEvery;      // backs off (x2, up to 64) while the scans keep reporting busy content
+    unsigned probe_every = kCalmProbeEvery;
+    // resident plan (poppy_cuda_set_plan): the packed triangle lists of a whole sequence in HBM, validated once
+    int3* d_plan_tri = nullptr;
+    size_t plan_cap = 0;                     // triangles d_plan_tri holds
+    std::vector<int32_t> plan_off;           // n + 1 offsets (triangles), plan_off[0] == 0
+    int plan_points = -1;                    // n_points the plan was validated against      // backs off (x2, up to 64) while the scans keep reporting busy content
     int mm_pitch = 0;                        // blocks per row of the clamp-excess table, padded
     size_t mm_stride = 0;
     unsigned long long* d_calm_total = nullptr;      // flagged strip chunks since the last stats read
@@ -355,6 +360,8 @@ void harvest_calm_stats(poppy_cuda_ctx* c, bool wait) {
     }
 }
 
+// tri_idx == nullptr: the triangles come from the resident plan, tri_off pointing into its offsets (frame `first` of this call
+// is plan frame plan_first + first)
 int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* shape, const double* mask, const int32_t* tri_idx,
                  const int32_t* tri_off, bool chain, poppy_cuda_ctx::Lane& ln) {
     cudaStream_t st = ln.stream;
@@ -366,8 +373,8 @@ int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* s
         const int f = first + i;
         const int nt = tri_off[f + 1] - tri_off[f];
         if (nt < 0 || nt > c->max_tri) return fail(c, POPPY_CUDA_ERR_CAPACITY, "frame %d has %d triangles (max %d)", f, nt, c->max_tri);
-        const int32_t* src = tri_idx + (size_t)tri_off[f] * 3;        // validated by poppy_cuda_render_range
-        if (nt) std::memcpy(ht + (size_t)tri_total * 3, src, (size_t)nt * 3 * sizeof(int32_t));
+        if (tri_idx && nt)         // validated by poppy_cuda_render_range
+            std::memcpy(ht + (size_t)tri_total * 3, tri_idx + (size_t)tri_off[f] * 3, (size_t)nt * 3 * sizeof(int32_t));
         FrameParams& p = hp[i];
         p.shape = shape[f];
         p.one_minus_r = (float)(1.0 - (double)p.shape);
@@ -381,8 +388,11 @@ int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* s
         tri_max = std::max(tri_max, nt);
     }
     CU_TRY(c, cudaMemcpyAsync(ln.d_fp, hp, nb * sizeof(FrameParams), cudaMemcpyHostToDevice, st));
-    if (tri_total) CU_TRY(c, cudaMemcpyAsync(ln.d_tri, ht, (size_t)tri_total * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (tri_idx && tri_total)
+        CU_TRY(c, cudaMemcpyAsync(ln.d_tri, ht, (size_t)tri_total * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CU_TRY(c, cudaEventRecord(ln.ev_staged, st));
+    // the chunk's packed triangles: the lane's staging copy, or their place in the resident plan (same packing)
+    const int3* chunk_tri = tri_idx ? ln.d_tri : c->d_plan_tri + tri_off[first];
 
     // a chain continues from the frame before it: the previous frame of this call, or - when a chain is rendered slice by
     // slice - the last frame of the previous call (ring slot slot0 + first - 1, whose pixels are still in t_src[2])
@@ -397,7 +407,7 @@ int render_chunk(poppy_cuda_ctx* c, int slot0, int first, int nb, const float* s
     }
     CU_TRY(c, cudaMemsetAsync(ln.d_tile_cnt, 0, (size_t)nb * c->n_tiles * sizeof(int), st));
     {   Scope s(c, KC_GEOMETRY, st);
-        launch_tri_geometry(st, ln.d_tri, ln.d_fp, p1, 0, c->d_pts2, morphed, c->max_points, c->max_tri, tri_max, nb, w, h,
+        launch_tri_geometry(st, chunk_tri, ln.d_fp, p1, 0, c->d_pts2, morphed, c->max_points, c->max_tri, tri_max, nb, w, h,
                             ln.d_inv, ln.d_rast, ln.d_tile_cnt);
     }
     {   Scope s(c, KC_BIN, st);
@@ -634,7 +644,7 @@ void poppy_cuda_destroy(poppy_cuda_ctx* c) {
     }
     cudaFree(c->d_pts1_raw); cudaFree(c->d_pts2_raw); cudaFree(c->d_pts1); cudaFree(c->d_pts2); cudaFree(c->d_morphed);
     cudaFree(c->d_tail_levels);
-    cudaFree(c->d_frames); cudaFree(c->d_sum); cudaFree(c->d_calm_total); cudaFree(c->d_probe_total);
+    cudaFree(c->d_frames); cudaFree(c->d_sum); cudaFree(c->d_calm_total); cudaFree(c->d_probe_total); cudaFree(c->d_plan_tri);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
@@ -795,22 +805,8 @@ int poppy_cuda_render(poppy_cuda_ctx* c, int n_frames, const float* shape, const
     return poppy_cuda_render_range(c, 0, n_frames, shape, mask, tri_idx, tri_off, chain);
 }
 
-int poppy_cuda_render_range(poppy_cuda_ctx* c, int first_slot, int n_frames, const float* shape, const double* mask,
-                            const int32_t* tri_idx, const int32_t* tri_off, int chain) {
-    if (!c) return POPPY_CUDA_ERR_INVALID;
-    if (first_slot < 0) return fail(c, POPPY_CUDA_ERR_INVALID, "bad first_slot %d", first_slot);
-    if (chain && first_slot > 0 && c->chain_next_slot != first_slot)
-        return fail(c, POPPY_CUDA_ERR_STATE, "a chain continues at the slot after its last rendered frame (%d), not at %d", c->chain_next_slot, first_slot);
-    if (!c->have_pair || !c->have_points) return fail(c, POPPY_CUDA_ERR_STATE, "set_pair and set_points must precede render");
-    if (!shape || !mask || !tri_off) return fail(c, POPPY_CUDA_ERR_INVALID, "null argument");
-    if (!tri_idx && n_frames >= 1 && tri_off[n_frames] != tri_off[0]) return fail(c, POPPY_CUDA_ERR_INVALID, "null triangle list");
-    if (n_frames < 1 || first_slot + n_frames > c->max_frames)
-        return fail(c, POPPY_CUDA_ERR_CAPACITY, "frames [%d, %d) exceed the ring (max %d)", first_slot, first_slot + n_frames, c->max_frames);
-    CU_TRY(c, cudaSetDevice(c->device));
-    if (int rc = ensure_chunk(c)) return rc;
-    if (first_slot < c->copy_hi && first_slot + n_frames > c->copy_lo)      // slots with a download in flight
-        CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
-    // validate every frame before anything is enqueued: a failure must not leave earlier chunks running on the lanes
+namespace {
+int validate_plan(poppy_cuda_ctx* c, const int32_t* tri_idx, const int32_t* tri_off, int n_frames) {
     for (int f = 0; f < n_frames; ++f) {
         const int nt = tri_off[f + 1] - tri_off[f];
         if (nt < 0 || nt > c->max_tri) return fail(c, POPPY_CUDA_ERR_CAPACITY, "frame %d has %d triangles (max %d)", f, nt, c->max_tri);
@@ -819,6 +815,78 @@ int poppy_cuda_render_range(poppy_cuda_ctx* c, int first_slot, int n_frames, con
             if ((unsigned)src[j] >= (unsigned)c->n_points)
                 return fail(c, POPPY_CUDA_ERR_INVALID, "frame %d: vertex index %d out of range [0,%d)", f, src[j], c->n_points);
     }
+    return 0;
+}
+int render_impl(poppy_cuda_ctx* c, int first_slot, int n_frames, const float* shape, const double* mask, const int32_t* tri_idx,
+                const int32_t* tri_off, int chain);
+}  // namespace
+
+int poppy_cuda_set_plan(poppy_cuda_ctx* c, const int32_t* tri_idx, const int32_t* tri_off, int n_frames) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (!c->have_points) return fail(c, POPPY_CUDA_ERR_STATE, "set_points must precede set_plan (vertex indices are checked against it)");
+    if (!tri_off || n_frames < 1) return fail(c, POPPY_CUDA_ERR_INVALID, "bad plan");
+    const size_t total = (size_t)(tri_off[n_frames] - tri_off[0]);
+    if (!tri_idx && total) return fail(c, POPPY_CUDA_ERR_INVALID, "null triangle list");
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (int rc = validate_plan(c, tri_idx, tri_off, n_frames)) return rc;
+    // nothing queued may still read the plan it replaces
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    for (auto& l : c->lane) if (l.stream) CU_TRY(c, cudaStreamSynchronize(l.stream));
+    if (total > c->plan_cap) {
+        cudaFree(c->d_plan_tri);
+        c->d_plan_tri = nullptr;
+        c->plan_cap = 0;
+        CU_TRY(c, dmalloc(&c->d_plan_tri, total));
+        c->plan_cap = total;
+    }
+    if (total)
+        CU_TRY(c, cudaMemcpy(c->d_plan_tri, tri_idx + (size_t)tri_off[0] * 3, total * sizeof(int3), cudaMemcpyHostToDevice));
+    c->plan_off.resize((size_t)n_frames + 1);
+    for (int f = 0; f <= n_frames; ++f) c->plan_off[f] = tri_off[f] - tri_off[0];
+    c->plan_points = c->n_points;
+    return 0;
+}
+
+int poppy_cuda_render_planned(poppy_cuda_ctx* c, int first_slot, int plan_first, int n_frames, const float* shape, const double* mask,
+                              int chain) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (c->plan_off.empty() || c->plan_points != c->n_points)
+        return fail(c, POPPY_CUDA_ERR_STATE, "no resident plan for the current point set (poppy_cuda_set_plan after set_points)");
+    if (plan_first < 0 || n_frames < 1 || (size_t)plan_first + (size_t)n_frames > c->plan_off.size() - 1)
+        return fail(c, POPPY_CUDA_ERR_INVALID, "frames [%d, %d) are not in the resident plan (%d frames)", plan_first, plan_first + n_frames,
+                    (int)c->plan_off.size() - 1);
+    return render_impl(c, first_slot, n_frames, shape, mask, nullptr, c->plan_off.data() + plan_first, chain);
+}
+
+int poppy_cuda_render_range(poppy_cuda_ctx* c, int first_slot, int n_frames, const float* shape, const double* mask,
+                            const int32_t* tri_idx, const int32_t* tri_off, int chain) {
+    if (!c) return POPPY_CUDA_ERR_INVALID;
+    if (!tri_off) return fail(c, POPPY_CUDA_ERR_INVALID, "null argument");
+    if (!tri_idx && n_frames >= 1 && tri_off[n_frames] != tri_off[0]) return fail(c, POPPY_CUDA_ERR_INVALID, "null triangle list");
+    if (n_frames >= 1 && tri_idx) {
+        // validate every frame before anything is enqueued: a failure must not leave earlier chunks running on the lanes
+        if (!c->have_points) return fail(c, POPPY_CUDA_ERR_STATE, "set_pair and set_points must precede render");
+        if (int rc = validate_plan(c, tri_idx, tri_off, n_frames)) return rc;
+    }
+    // an empty triangle list still needs a non-null base for the chunk staging
+    static const int32_t none[3] = {0, 0, 0};
+    return render_impl(c, first_slot, n_frames, shape, mask, tri_idx ? tri_idx : none, tri_off, chain);
+}
+
+namespace {
+int render_impl(poppy_cuda_ctx* c, int first_slot, int n_frames, const float* shape, const double* mask, const int32_t* tri_idx,
+                const int32_t* tri_off, int chain) {
+    if (first_slot < 0) return fail(c, POPPY_CUDA_ERR_INVALID, "bad first_slot %d", first_slot);
+    if (chain && first_slot > 0 && c->chain_next_slot != first_slot)
+        return fail(c, POPPY_CUDA_ERR_STATE, "a chain continues at the slot after its last rendered frame (%d), not at %d", c->chain_next_slot, first_slot);
+    if (!c->have_pair || !c->have_points) return fail(c, POPPY_CUDA_ERR_STATE, "set_pair and set_points must precede render");
+    if (!shape || !mask || !tri_off) return fail(c, POPPY_CUDA_ERR_INVALID, "null argument");
+    if (n_frames < 1 || first_slot + n_frames > c->max_frames)
+        return fail(c, POPPY_CUDA_ERR_CAPACITY, "frames [%d, %d) exceed the ring (max %d)", first_slot, first_slot + n_frames, c->max_frames);
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (int rc = ensure_chunk(c)) return rc;
+    if (first_slot < c->copy_hi && first_slot + n_frames > c->copy_lo)      // slots with a download in flight
+        CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
     collect_timing(c);
     std::fill(c->class_ms, c->class_ms + KC_COUNT, 0.f);
     std::fill(c->class_launches, c->class_launches + KC_COUNT, 0ull);
@@ -850,6 +918,7 @@ int poppy_cuda_render_range(poppy_cuda_ctx* c, int first_slot, int n_frames, con
     c->chain_next_slot = chain ? first_slot + n_frames : -1;
     return 0;
 }
+}  // namespace
 
 int poppy_cuda_download(poppy_cuda_ctx* c, int first, int count, uint8_t* dst, size_t step, size_t frame_stride) {
     if (!c) return POPPY_CUDA_ERR_INVALID;

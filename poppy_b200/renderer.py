@@ -110,6 +110,25 @@ class MorphRenderer:
                                                       _ptr(tri_idx), _ptr(tri_offsets), 1 if chain else 0))
         return n
 
+    def set_plan(self, tri_idx, tri_offsets):
+        """Keep the triangle lists of a whole sequence resident in HBM (validated once); see render_planned."""
+        tri_idx = np.ascontiguousarray(tri_idx, np.int32).reshape(-1, 3)
+        tri_offsets = np.ascontiguousarray(tri_offsets, np.int32)
+        if tri_offsets[-1] - tri_offsets[0] > tri_idx.shape[0] - tri_offsets[0]:
+            raise ValueError("inconsistent triangle-offset array")
+        self._check(self._lib.poppy_cuda_set_plan(self._ctx, _ptr(tri_idx), _ptr(tri_offsets), tri_offsets.shape[0] - 1))
+
+    def render_planned(self, shape_ratio, mask_ratio, plan_first=0, chain=False, first_slot=0):
+        """Render len(shape_ratio) frames whose triangle lists are frames plan_first.. of the resident plan."""
+        shape_ratio = np.ascontiguousarray(shape_ratio, np.float32)
+        mask_ratio = np.ascontiguousarray(mask_ratio, np.float64)
+        n = shape_ratio.shape[0]
+        if mask_ratio.shape[0] != n:
+            raise ValueError("inconsistent frame arrays")
+        self._check(self._lib.poppy_cuda_render_planned(self._ctx, int(first_slot), int(plan_first), n, _ptr(shape_ratio),
+                                                        _ptr(mask_ratio), 1 if chain else 0))
+        return n
+
     def download(self, first, count, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:
             out = np.empty((count, self.height, self.width, 3), np.uint8)

@@ -330,3 +330,29 @@ def test_two_contexts_on_two_devices_in_one_process(native_lib):
         assert (api.blur_margin(inp.bgr1[:150, :300], (320, 200)) == api.blur_margin(inp.bgr1[:150, :300], (320, 200))).all()
     api.Settings.instance().cuda_device = 0
     assert (frames[0] == frames[1]).all() and (frames[0] == frames[2]).all()
+
+
+def test_resident_plan_renders_the_same_frames(native_lib):
+    """poppy_cuda_set_plan + render_planned (triangle lists validated and uploaded once) against render with host lists,
+    whole and in slices with a plan offset; a bad index is rejected at set_plan."""
+    from poppy_b200.renderer import MorphRenderer
+    w, h, L = 256, 160, 5
+    inp = synth.make_inputs(w, h, 120, 5.0, seed=77)
+    phases = np.linspace(0.05, 0.95, 11).astype(np.float32)
+    plan = host.SequencePlan(inp.pts1, inp.pts2, w, h, phases)
+    with MorphRenderer(w, h, L, len(inp.pts1), plan.max_triangles, len(phases), chunk_frames=3) as r:
+        r.set_pair(inp.bgr1, inp.bgr2, inp.gabor2)
+        r.set_points(inp.pts1, inp.pts2)
+        r.render(phases, phases.astype(np.float64), plan.tri_idx, plan.tri_offsets)
+        want = [r.checksum(k, 1) for k in range(len(phases))]
+        r.set_plan(plan.tri_idx, plan.tri_offsets)
+        r.render_planned(phases, phases.astype(np.float64))
+        assert [r.checksum(k, 1) for k in range(len(phases))] == want
+        r.render_planned(phases[4:9], phases[4:9].astype(np.float64), plan_first=4, first_slot=2)      # a slice into other slots
+        assert [r.checksum(2 + k, 1) for k in range(5)] == want[4:9]
+        with pytest.raises(RuntimeError):
+            r.render_planned(phases, phases.astype(np.float64), plan_first=3)                           # runs past the plan
+        bad = plan.tri_idx.copy()
+        bad[5, 1] = len(inp.pts1)
+        with pytest.raises(RuntimeError):
+            r.set_plan(bad, plan.tri_offsets)
